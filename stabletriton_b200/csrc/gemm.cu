@@ -1,0 +1,174 @@
+// C-ABI launchers for the tcgen05 GEMM / implicit-GEMM conv kernel (gemm_tc.cuh).
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace st {
+
+// Pick the B-tile width that minimises (waves x per-tile cost) on this device.  Tiles are 128 rows
+// tall; the per-tile cost model is (BLOCK_N + fixed overhead) -- MMA time scales with BLOCK_N, the
+// overhead term stands for pipeline fill and the non-overlapped part of the epilogue.
+static int choose_block_n(int M, int n_cols, bool geglu, int K) {
+  const int sms = device_sm_count();
+  const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
+  const int cands[3] = {256, 128, 64};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const int out_cols = geglu ? bn / 2 : bn;
+    const int nb = (n_cols + out_cols - 1) / out_cols;
+    const long tiles = (long)mb * nb;
+    const long waves = (tiles + sms - 1) / sms;
+    // per-tile: MMA cycles ~ bn * K/64 * (64/16) * ... proportional to bn*K; epilogue ~ out_cols; fill ~ const
+    const double tile_cost = (double)bn * K / 64.0 + 0.6 * bn + 24.0;
+    const double cost = waves * tile_cost;
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BLOCK_N, STAGES>;
+  auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(%d bytes) failed: %s", S::kTotal, cudaGetErrorString(e));
+      return ST_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  kernel<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, p);
+  ST_CHECK_LAUNCH("gemm_bf16_tc_kernel");
+  return ST_OK;
+}
+
+template <bool kConvA>
+static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int block_n, bool geglu,
+                         cudaStream_t stream) {
+  if (geglu) {
+    switch (block_n) {
+      case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, true>(ta, tb, p, stream);
+      case 64: return launch_gemm<64, 8, kConvA, true>(ta, tb, p, stream);
+    }
+  } else {
+    switch (block_n) {
+      case 256: return launch_gemm<256, 4, kConvA, false>(ta, tb, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, p, stream);
+      case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, p, stream);
+    }
+  }
+  set_error("gemm: unsupported block_n %d (use 0, 64, 128 or 256)", block_n);
+  return ST_ERR_INVALID_ARGUMENT;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace st
+
+extern "C" {
+
+int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ldd, int M, int N, int K,
+                 const void* bias, const void* residual, int ldr, unsigned flags, int block_n, st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(A && W && D, "gemm: null pointer");
+  ST_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M, N, K must be positive (got %d, %d, %d)", M, N, K);
+  ST_CHECK_ARG(K % kGemmBlockK == 0, "gemm: K (%d) must be a multiple of 64", K);
+  ST_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldd % 8 == 0, "gemm: row pitches must be multiples of 8 elements");
+  ST_CHECK_ARG(lda >= K && ldw >= K, "gemm: lda/ldw smaller than K");
+  ST_CHECK_ARG(aligned16(A) && aligned16(W) && aligned16(D), "gemm: pointers must be 16-byte aligned");
+  const bool geglu = (flags & ST_EPI_GEGLU) != 0;
+  ST_CHECK_ARG(!geglu || N % 2 == 0, "gemm: GEGLU needs an even N");
+  const int n_out = geglu ? N / 2 : N;
+  ST_CHECK_ARG(n_out % 8 == 0, "gemm: output width (%d) must be a multiple of 8", n_out);
+  ST_CHECK_ARG(ldd >= n_out, "gemm: ldd smaller than the output width");
+  ST_CHECK_ARG(!bias || aligned16(bias), "gemm: bias must be 16-byte aligned");
+  ST_CHECK_ARG(!residual || (aligned16(residual) && ldr % 8 == 0 && ldr >= n_out), "gemm: bad residual pitch/alignment");
+  ST_CHECK_ARG(!(geglu && (flags & ST_EPI_SILU)), "gemm: GEGLU and SiLU epilogues are exclusive");
+
+  if (block_n == 0) block_n = choose_block_n(M, n_out, geglu, K);
+  const int out_cols = geglu ? block_n / 2 : block_n;
+
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.n_out = n_out;
+  p.ldd = ldd;
+  p.num_m_blocks = (M + kGemmBlockM - 1) / kGemmBlockM;
+  p.num_n_blocks = (n_out + out_cols - 1) / out_cols;
+  p.D = static_cast<__nv_bfloat16*>(D);
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.ldr = ldr;
+  p.rowbias = nullptr;
+  p.rows_per_batch = 1;
+  p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, A, M, K, lda, kGemmBlockM);
+  if (rc != ST_OK) return rc;
+  rc = make_tmap_2d(&tb, W, N, K, ldw, geglu ? block_n / 2 : block_n);
+  if (rc != ST_OK) return rc;
+  return dispatch_gemm<false>(ta, tb, p, block_n, geglu, static_cast<cudaStream_t>(stream));
+}
+
+int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int C, int K,
+                         const void* temb, int ld_temb, const void* residual, unsigned flags, int block_n,
+                         st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(x && w && y, "conv3x3: null pointer");
+  ST_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && K > 0, "conv3x3: sizes must be positive");
+  ST_CHECK_ARG(C % 64 == 0, "conv3x3: C (%d) must be a multiple of 64 (use st_conv3x3_direct_nhwc_bf16)", C);
+  ST_CHECK_ARG(K % 8 == 0, "conv3x3: K (%d) must be a multiple of 8", K);
+  ST_CHECK_ARG((H * W) % kGemmBlockM == 0, "conv3x3: H*W (%d) must be a multiple of 128", H * W);
+  int Wt = W < 128 ? W : 128;
+  ST_CHECK_ARG(W % Wt == 0 && 128 % Wt == 0, "conv3x3: unsupported width %d", W);
+  const int Ht = 128 / Wt;
+  ST_CHECK_ARG(H % Ht == 0, "conv3x3: unsupported height %d for width %d", H, W);
+  ST_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y), "conv3x3: pointers must be 16-byte aligned");
+  ST_CHECK_ARG(!(flags & ST_EPI_GEGLU), "conv3x3: GEGLU epilogue not supported");
+  ST_CHECK_ARG(!temb || (aligned16(temb) && ld_temb % 8 == 0), "conv3x3: bad temb pitch/alignment");
+
+  const int M = N * H * W;
+  if (block_n == 0) block_n = choose_block_n(M, K, false, 9 * C);
+
+  GemmParams p{};
+  p.M = M;
+  p.N = K;
+  p.K = 9 * C;
+  p.n_out = K;
+  p.ldd = K;
+  p.num_m_blocks = M / kGemmBlockM;
+  p.num_n_blocks = (K + block_n - 1) / block_n;
+  p.D = static_cast<__nv_bfloat16*>(y);
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.ldr = K;
+  p.rowbias = static_cast<const __nv_bfloat16*>(temb);
+  p.ld_rowbias = ld_temb;
+  p.rows_per_batch = H * W;
+  p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
+  p.conv_H = H;
+  p.conv_W = W;
+  p.conv_C = C;
+  p.conv_Wt = Wt;
+  p.conv_Ht = Ht;
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_nhwc(&ta, x, N, H, W, C, Ht, Wt);
+  if (rc != ST_OK) return rc;
+  rc = make_tmap_2d(&tb, w, K, 9 * (uint64_t)C, 9 * (uint64_t)C, block_n);
+  if (rc != ST_OK) return rc;
+  return dispatch_gemm<true>(ta, tb, p, block_n, false, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// Bandwidth-bound normalisation kernels: GroupNorm(+SiLU) on NHWC and LayerNorm over the last dim.
+// 128-bit coalesced loads/stores, fp32 statistics (shifted sums per thread, Chan/Welford merges
+// across threads / CTAs), one HBM read + one write of the activation (the second GroupNorm read is
+// served by the 126 MB L2).
+//
+// Replaces (reference): kernels/groupnorm.py:24-161 (semantics fixed to torch.nn.GroupNorm on 4-D
+// input) and kernels/layer_norm.py:114-346.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace st {
+
+struct Welford {
+  float n, mean, m2;
+};
+
+__device__ __forceinline__ Welford welford_merge(Welford a, Welford b) {
+  if (b.n == 0.f) return a;
+  if (a.n == 0.f) return b;
+  Welford r;
+  r.n = a.n + b.n;
+  const float d = b.mean - a.mean;
+  const float f = b.n / r.n;
+  r.mean = a.mean + d * f;
+  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  return r;
+}
+
+__device__ __forceinline__ uint4 ld_nc_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16x2(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm
+//   workspace layout (floats):  partial[N][chunks][G][3] (n, mean, M2)  |  scale_shift[N][C][2]
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnMaxThreads = 512;
+
+struct GnGeom {
+  int N, HW, C, G, cpg;
+  int vecs;          // C / 8 : 16-byte vectors per pixel
+  int threads;       // multiple of vecs, <= 512
+  int pix_lanes;     // threads / vecs
+  int chunks;        // CTAs per image
+  int pix_per_chunk; // ceil(HW / chunks)
+};
+
+static GnGeom gn_geometry(int N, int HW, int C, int G) {
+  GnGeom g;
+  g.N = N;
+  g.HW = HW;
+  g.C = C;
+  g.G = G;
+  g.cpg = C / G;
+  g.vecs = C / 8;
+  g.pix_lanes = kGnMaxThreads / g.vecs;
+  if (g.pix_lanes < 1) g.pix_lanes = 1;
+  g.threads = g.pix_lanes * g.vecs;
+  // enough CTAs for ~4 per SM, but at least 4 passes of work per CTA
+  const int sms = device_sm_count();
+  int chunks = (4 * sms + N - 1) / N;
+  const int max_chunks = (HW + 4 * g.pix_lanes - 1) / (4 * g.pix_lanes);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  g.pix_per_chunk = (HW + chunks - 1) / chunks;
+  g.chunks = (HW + g.pix_per_chunk - 1) / g.pix_per_chunk;
+  return g;
+}
+
+// Pass 1: per-CTA partial statistics of every group over a range of pixels.
+__global__ void __launch_bounds__(kGnMaxThreads)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int cpg,
+                int vecs, int pix_lanes, int pix_per_chunk) {
+  extern __shared__ float s_part[];  // [threads][2][4] : (group, n, mean, m2) for the <=2 groups of a vector
+  const int n = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int cv = threadIdx.x % vecs;
+  const int pl = threadIdx.x / vecs;
+  const int pb = chunk * pix_per_chunk;
+  const int pe = min(pb + pix_per_chunk, HW);
+  const __nv_bfloat16* base = x + (static_cast<size_t>(n) * HW) * C + cv * 8;
+
+  // shifted sums: shift = first value this thread sees, per channel (robust to |mean| >> std)
+  float shift[8], s1[8], s2[8];
+  float cnt = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) shift[e] = s1[e] = s2[e] = 0.f;
+  int pix = pb + pl;
+  if (pix < pe) {
+    float f[8];
+    unpack8(ld_nc_16(base + static_cast<size_t>(pix) * C), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) shift[e] = f[e];
+    cnt = 1.f;
+    pix += pix_lanes;
+  }
+  for (; pix + 3 * pix_lanes < pe; pix += 4 * pix_lanes) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = ld_nc_16(base + static_cast<size_t>(pix + i * pix_lanes) * C);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float f[8];
+      unpack8(u[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[e] - shift[e];
+        s1[e] += d;
+        s2[e] = fmaf(d, d, s2[e]);
+      }
+    }
+    cnt += 4.f;
+  }
+  for (; pix < pe; pix += pix_lanes) {
+    float f[8];
+    unpack8(ld_nc_16(base + static_cast<size_t>(pix) * C), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = f[e] - shift[e];
+      s1[e] += d;
+      s2[e] = fmaf(d, d, s2[e]);
+    }
+    cnt += 1.f;
+  }
+
+  // per-channel (n, mean, M2) -> merge the 8 channels into the (at most two) groups they belong to
+  const int c0 = cv * 8;
+  const int g_lo = c0 / cpg;
+  const int g_hi = (c0 + 7) / cpg;
+  Welford w_lo{0.f, 0.f, 0.f}, w_hi{0.f, 0.f, 0.f};
+  if (cnt > 0.f) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      Welford w;
+      w.n = cnt;
+      const float m = s1[e] / cnt;
+      w.mean = shift[e] + m;
+      w.m2 = fmaxf(s2[e] - s1[e] * m, 0.f);
+      if ((c0 + e) / cpg == g_lo)
+        w_lo = welford_merge(w_lo, w);
+      else
+        w_hi = welford_merge(w_hi, w);
+    }
+  }
+  float* sp = s_part + threadIdx.x * 8;
+  sp[0] = __int_as_float(g_lo);
+  sp[1] = w_lo.n;
+  sp[2] = w_lo.mean;
+  sp[3] = w_lo.m2;
+  sp[4] = __int_as_float(g_hi == g_lo ? -1 : g_hi);
+  sp[5] = w_hi.n;
+  sp[6] = w_hi.mean;
+  sp[7] = w_hi.m2;
+  __syncthreads();
+
+  // one thread per group gathers the partials of the vectors overlapping its channels
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const int v_lo = (g * cpg) / 8;
+    const int v_hi = (g * cpg + cpg - 1) / 8;
+    Welford acc{0.f, 0.f, 0.f};
+    for (int l = 0; l < pix_lanes; ++l) {
+      for (int v = v_lo; v <= v_hi; ++v) {
+        const float* q = s_part + (l * vecs + v) * 8;
+        if (__float_as_int(q[0]) == g) acc = welford_merge(acc, Welford{q[1], q[2], q[3]});
+        if (__float_as_int(q[4]) == g) acc = welford_merge(acc, Welford{q[5], q[6], q[7]});
+      }
+    }
+    float* out = partial + ((static_cast<size_t>(n) * gridDim.x + chunk) * G + g) * 3;
+    out[0] = acc.n;
+    out[1] = acc.mean;
+    out[2] = acc.m2;
+  }
+}
+
+// Pass 2: merge chunk partials per (image, group) and emit per-channel scale/shift:
+//   y = x * scale_c + shift_c,  scale_c = gamma_c * rstd_g,  shift_c = beta_c - mean_g * scale_c
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma,
+                                   const __nv_bfloat16* __restrict__ beta, float* __restrict__ scale_shift, int chunks,
+                                   int C, int G, int cpg, float eps) {
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  for (int g = warp; g < G; g += warps) {
+    Welford acc{0.f, 0.f, 0.f};
+    for (int c = lane; c < chunks; c += 32) {
+      const float* q = partial + ((static_cast<size_t>(n) * chunks + c) * G + g) * 3;
+      acc = welford_merge(acc, Welford{q[0], q[1], q[2]});
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Welford other;
+      other.n = __shfl_xor_sync(0xffffffffu, acc.n, o);
+      other.mean = __shfl_xor_sync(0xffffffffu, acc.mean, o);
+      other.m2 = __shfl_xor_sync(0xffffffffu, acc.m2, o);
+      acc = welford_merge(acc, other);
+    }
+    const float var = acc.m2 / acc.n;  // biased, as torch.nn.GroupNorm
+    const float rstd = rsqrtf(var + eps);
+    for (int c = lane; c < cpg; c += 32) {
+      const int ch = g * cpg + c;
+      const float ga = gamma ? __bfloat162float(gamma[ch]) : 1.f;
+      const float be = beta ? __bfloat162float(beta[ch]) : 0.f;
+      const float sc = ga * rstd;
+      float* o = scale_shift + (static_cast<size_t>(n) * C + ch) * 2;
+      o[0] = sc;
+      o[1] = be - acc.mean * sc;
+    }
+  }
+}
+
+// Pass 3: y = silu?(x * scale + shift), streaming.
+template <bool kSilu>
+__global__ void __launch_bounds__(kGnMaxThreads)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                const float* __restrict__ scale_shift, int HW, int C, int vecs, int pix_lanes, int pix_per_chunk) {
+  const int n = blockIdx.y;
+  const int cv = threadIdx.x % vecs;
+  const int pl = threadIdx.x / vecs;
+  const int pb = blockIdx.x * pix_per_chunk;
+  const int pe = min(pb + pix_per_chunk, HW);
+  float sc[8], sh[8];
+  {
+    const float4* q = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(n) * C + cv * 8) * 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = q[i];
+      sc[2 * i] = t.x;
+      sh[2 * i] = t.y;
+      sc[2 * i + 1] = t.z;
+      sh[2 * i + 1] = t.w;
+    }
+  }
+  const size_t img = (static_cast<size_t>(n) * HW) * C + cv * 8;
+  const __nv_bfloat16* xb = x + img;
+  __nv_bfloat16* yb = y + img;
+  for (int pix = pb + pl; pix < pe; pix += 4 * pix_lanes) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = pix + i * pix_lanes;
+      if (pp < pe) u[i] = ld_nc_16(xb + static_cast<size_t>(pp) * C);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = pix + i * pix_lanes;
+      if (pp < pe) {
+        float f[8];
+        unpack8(u[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = fmaf(f[e], sc[e], sh[e]);
+          if (kSilu) v = silu_f(v);
+          f[e] = v;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pp) * C) = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (two-pass statistics, exact).
+// ------------------------------------------------------------------------------------------------
+template <int kVecsPerLane>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
+                 const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int M, int N,
+                 float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const int nvec = N >> 3;
+  const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
+  float f[kVecsPerLane][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecsPerLane; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      unpack8(ld_nc_16(xr + v * 8), f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += f[i][e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / N;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecsPerLane; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[i][e] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / N + eps);
+  __nv_bfloat16* yr = y + static_cast<size_t>(row) * ldy;
+#pragma unroll
+  for (int i = 0; i < kVecsPerLane; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float g[8], b[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), g);
+      if (beta) {
+        unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), b);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) b[e] = 0.f;
+      }
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf((f[i][e] - mean) * rstd, g[e], b[e]);
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]);
+      u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + v * 8) = u;
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace st
+
+extern "C" {
+
+size_t st_groupnorm_workspace_bytes(int N, int HW, int C, int groups) {
+  if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0 || C % 8 != 0) return 0;
+  const st::GnGeom g = st::gn_geometry(N, HW, C, groups);
+  const size_t partial = static_cast<size_t>(N) * g.chunks * groups * 3;
+  const size_t ss = static_cast<size_t>(N) * C * 2;
+  return ((partial + 3) / 4 * 4 + ss) * sizeof(float);
+}
+
+int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, void* workspace, int N,
+                           int HW, int C, int groups, float eps, int apply_silu, st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(x && y && workspace, "groupnorm: null pointer");
+  ST_CHECK_ARG(N > 0 && HW > 0 && C > 0 && groups > 0, "groupnorm: sizes must be positive");
+  ST_CHECK_ARG(C % groups == 0, "groupnorm: C (%d) not divisible by groups (%d)", C, groups);
+  ST_CHECK_ARG(C % 8 == 0, "groupnorm: C (%d) must be a multiple of 8", C);
+  ST_CHECK_ARG(C / 8 <= kGnMaxThreads, "groupnorm: C (%d) too large (max %d)", C, 8 * kGnMaxThreads);
+  ST_CHECK_ARG(C / groups >= 7 || C / groups == 4,
+               "groupnorm: %d channels per group unsupported (a 16-byte vector may span at most two groups)", C / groups);
+  ST_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(workspace), "groupnorm: pointers must be 16-byte aligned");
+  const GnGeom g = gn_geometry(N, HW, C, groups);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  const size_t partial_elems = (static_cast<size_t>(N) * g.chunks * groups * 3 + 3) / 4 * 4;
+  float* scale_shift = partial + partial_elems;
+
+  const dim3 grid(g.chunks, N);
+  const size_t smem = static_cast<size_t>(g.threads) * 8 * sizeof(float);
+  gn_stats_kernel<<<grid, g.threads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), partial, HW, C, groups, g.cpg,
+                                                g.vecs, g.pix_lanes, g.pix_per_chunk);
+  ST_CHECK_LAUNCH("gn_stats_kernel");
+  gn_finalize_kernel<<<N, 256, 0, s>>>(partial, static_cast<const __nv_bfloat16*>(gamma),
+                                       static_cast<const __nv_bfloat16*>(beta), scale_shift, g.chunks, C, groups, g.cpg,
+                                       eps);
+  ST_CHECK_LAUNCH("gn_finalize_kernel");
+  if (apply_silu)
+    gn_apply_kernel<true><<<grid, g.threads, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+                                                     static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs,
+                                                     g.pix_lanes, g.pix_per_chunk);
+  else
+    gn_apply_kernel<false><<<grid, g.threads, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+                                                      static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs,
+                                                      g.pix_lanes, g.pix_per_chunk);
+  ST_CHECK_LAUNCH("gn_apply_kernel");
+  return ST_OK;
+}
+
+int st_layernorm_bf16(const void* x, int ldx, void* y, int ldy, const void* gamma, const void* beta, int M, int N,
+                      float eps, st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(x && y && gamma, "layernorm: null pointer");
+  ST_CHECK_ARG(M > 0 && N > 0, "layernorm: sizes must be positive");
+  ST_CHECK_ARG(N % 8 == 0 && N <= 4096, "layernorm: N (%d) must be a multiple of 8 and <= 4096", N);
+  ST_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= N && ldy >= N, "layernorm: bad row pitch");
+  ST_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && (!beta || aligned16(beta)),
+               "layernorm: pointers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows_per_cta = 8;
+  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  const int vpl = (N / 8 + 31) / 32;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(gamma);
+  const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(beta);
+#define ST_LN_CASE(V)                                                                    \
+  case V:                                                                                \
+    layernorm_kernel<V><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gp, bp, M, N, eps);       \
+    break;
+  switch (vpl <= 3 ? 3 : vpl <= 5 ? 5 : vpl <= 8 ? 8 : 16) {
+    ST_LN_CASE(3)
+    ST_LN_CASE(5)
+    ST_LN_CASE(8)
+    ST_LN_CASE(16)
+  }
+#undef ST_LN_CASE
+  ST_CHECK_LAUNCH("layernorm_kernel");
+  return ST_OK;
+}
+
+}  // extern "C"
