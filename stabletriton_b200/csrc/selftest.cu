@@ -92,18 +92,31 @@ static void report(const char* name, const std::vector<float>& got, const std::v
   if (!ok) ++g_fail;
 }
 
+// Device time per call: `iters` calls captured into one CUDA graph and replayed, so host-side launch
+// cost (tensor-map encoding, driver submit) is excluded -- the product runs inside a graph too.
+// Note: back-to-back replays reuse the same buffers, so small cases are L2-warm.
+static cudaStream_t g_stream = nullptr;
 template <typename F>
 static float time_ms(F f, int warm = 2, int iters = 10) {
-  for (int i = 0; i < warm; ++i) f();
+  if (!g_stream) CK(cudaStreamCreate(&g_stream));
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeGlobal));
+  for (int i = 0; i < iters; ++i) f(g_stream);
+  CK(cudaStreamEndCapture(g_stream, &graph));
+  CK(cudaGraphInstantiate(&exec, graph, 0));
+  for (int i = 0; i < warm; ++i) CK(cudaGraphLaunch(exec, g_stream));
   cudaEvent_t a, b;
   CK(cudaEventCreate(&a));
   CK(cudaEventCreate(&b));
-  CK(cudaEventRecord(a));
-  for (int i = 0; i < iters; ++i) f();
-  CK(cudaEventRecord(b));
+  CK(cudaEventRecord(a, g_stream));
+  CK(cudaGraphLaunch(exec, g_stream));
+  CK(cudaEventRecord(b, g_stream));
   CK(cudaEventSynchronize(b));
   float ms;
   CK(cudaEventElapsedTime(&ms, a, b));
+  CK(cudaGraphExecDestroy(exec));
+  CK(cudaGraphDestroy(graph));
   return ms / iters;
 }
 
@@ -204,7 +217,7 @@ static void test_gemm_case(int M, int N, int K, unsigned flags, bool bias, bool 
   ref_gemm<<<dim3((n_out + 127) / 128, M), 128>>>(A, K, W, K, Dref, M, N, K, b, r, n_out, flags);
   CK(cudaDeviceSynchronize());
   float ms = -1;
-  if (timeit) ms = time_ms([&] { st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, block_n, 0); });
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, block_n, s); });
   char name[128];
   snprintf(name, sizeof name, "gemm M=%d N=%d K=%d flags=%u bias=%d res=%d bn=%d", M, N, K, flags, bias, res, block_n);
   report(name, to_host(D, (size_t)M * n_out), to_host_f(Dref, (size_t)M * n_out), 1e-2f, ms, 2.0 * M * N * K * 1e-12,
@@ -260,7 +273,7 @@ static void test_conv_case(int N, int H, int W, int C, int K, bool temb, bool re
   ref_conv3x3<<<dim3((K + 127) / 128, N * H * W), 128>>>(x, w, b, yref, N, H, W, C, K, t, r);
   CK(cudaDeviceSynchronize());
   float ms = -1;
-  if (timeit) ms = time_ms([&] { st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, 0, block_n, 0); });
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, 0, block_n, s); });
   char name[128];
   snprintf(name, sizeof name, "conv3x3 N=%d H=%d W=%d C=%d K=%d temb=%d res=%d bn=%d", N, H, W, C, K, temb, res,
            block_n);
@@ -314,7 +327,7 @@ static void test_attn_case(int B, int H, int Tq, int Tk, bool fused_qkv, bool ti
   ref_attention<<<dim3((Tq + 63) / 64, B * H), 64>>>(q, ld, k, ld, v, ld, oref, B, H, Tq, Tk, scale);
   CK(cudaDeviceSynchronize());
   float ms = -1;
-  if (timeit) ms = time_ms([&] { st_attention_bf16(q, ld, k, ld, v, ld, o, C, B, H, Tq, Tk, scale, 0); });
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_attention_bf16(q, ld, k, ld, v, ld, o, C, B, H, Tq, Tk, scale, s); });
   char name[128];
   snprintf(name, sizeof name, "attention B=%d H=%d Tq=%d Tk=%d fusedqkv=%d", B, H, Tq, Tk, fused_qkv);
   report(name, to_host(o, out), to_host_f(oref, out), 2e-2f, ms, 4.0 * B * H * (double)Tq * Tk * 64 * 1e-12,
@@ -386,7 +399,7 @@ static void test_groupnorm_case(int N, int HW, int C, int G, bool silu, float of
         }
     }
   float ms = -1;
-  if (timeit) ms = time_ms([&] { st_groupnorm_nhwc_bf16(x, y, g, b, ws, N, HW, C, G, 1e-5f, silu, 0); }, 2, 20);
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_groupnorm_nhwc_bf16(x, y, g, b, ws, N, HW, C, G, 1e-5f, silu, s); }, 2, 20);
   char name[128];
   snprintf(name, sizeof name, "groupnorm N=%d HW=%d C=%d G=%d silu=%d off=%.0f", N, HW, C, G, silu, offset);
   report(name, to_host(y, ref.size()), ref, 1.5e-2f, ms, 4.0 * N * HW * (double)C * 1e-9, "GB/s");
@@ -419,7 +432,7 @@ static void test_layernorm_case(int M, int N, bool timeit) {
     for (int n = 0; n < N; ++n) ref[(size_t)m * N + n] = (float)((hx[(size_t)m * N + n] - mean) * rstd * hg[n] + hb[n]);
   }
   float ms = -1;
-  if (timeit) ms = time_ms([&] { st_layernorm_bf16(x, N, y, N, g, b, M, N, 1e-5f, 0); }, 2, 20);
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_layernorm_bf16(x, N, y, N, g, b, M, N, 1e-5f, s); }, 2, 20);
   char name[128];
   snprintf(name, sizeof name, "layernorm M=%d N=%d", M, N);
   report(name, to_host(y, ref.size()), ref, 1e-2f, ms, 4.0 * M * (double)N * 1e-9, "GB/s");
