@@ -76,7 +76,7 @@ int st_geglu_bf16(const void* state, int ld_state, const void* gate, int ld_gate
 int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ldd, int M, int N, int K,
                  const void* bias, const void* residual, int ldr, unsigned flags, int block_n, st_stream_t stream);
 
-/* Tiny-M Linear (time / added-condition embeddings, M <= 16): y = act_out(act_in(x) . W^T + b).
+/* Tiny-M Linear (time / added-condition embeddings, M <= 32): y = act_out(act_in(x) . W^T + b).
  * CUDA-core, weight-bandwidth bound.  silu_in applies SiLU to x on load (unet_pt.py:81-82). */
 int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const void* bias, void* y, int ldy, int M,
                            int N, int K, int silu_in, int silu_out, st_stream_t stream);
@@ -109,10 +109,15 @@ int st_upsample_nearest2x_nhwc_bf16(const void* x, void* y, int N, int H, int W,
 /* ---- Multi-head attention forward (flash, online softmax), head_dim 64 --------------------------
  * Implements the *pattern* of fuse_attention (reference: optimizers/replace_attention.py:76-86):
  * per head softmax(Q K^T * scale) V, heads = channels [64h, 64h+64) of (B, T, H*64) tensors, no mask.
- * q: [B, Tq, H*64] with row pitch ldq (elements), k/v: [B, Tk, H*64] with pitches ldk/ldv, o: pitch ldo.
- * Separate Tq / Tk and a masked K tail make cross-attention (Tk = 77) work. */
-int st_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
-                      int H, int Tq, int Tk, float scale, st_stream_t stream);
+ * Every tensor is addressed as [b][h][t][d] through element strides (sb, sh, st) with d contiguous:
+ * (B, T, H*64) activations use sh = 64, st = row pitch, sb = T*pitch (so q/k/v may be column slices of one
+ * fused QKV buffer); the reference's (B, H, T, D) layout (kernels/attention_fa2.py:113-140) uses
+ * st = 64, sh = T*64.  Strides % 8 == 0.  Separate Tq / Tk and a masked K tail make cross-attention
+ * (Tk = 77) work. */
+int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q_st, const void* k, long long k_sb,
+                      long long k_sh, long long k_st, const void* v, long long v_sb, long long v_sh, long long v_st,
+                      void* o, long long o_sb, long long o_sh, long long o_st, int B, int H, int Tq, int Tk,
+                      float scale, st_stream_t stream);
 
 /* ---- elementwise glue -------------------------------------------------------------------------
  * Sinusoidal timestep embedding (unet_pt.py:22-36): out[b, :] = cat(cos(t_b * f_i), sin(t_b * f_i)),

@@ -27,7 +27,7 @@ constexpr int kAttnSmemBytes = kAttnTileBytes * (1 + 2 * kAttnStages + 4) + 1024
 
 struct AttnParams {
   __nv_bfloat16* O;
-  int ldo;
+  long long o_sb, o_sh, o_st;
   int H, Tq, Tk;
   float scale_log2;
 };
@@ -89,15 +89,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       mbar_expect_tx(q_full, kAttnTileBytes);
-      tma_load_3d(sQ, &tmap_q, q_full, h * kAttnD, q0, b);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kAttnStages;
         const uint32_t ph = (j / kAttnStages) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], kAttnTileBytes);
-        tma_load_3d(sK + st * kAttnTileBytes, &tmap_k, &k_full[st], h * kAttnD, j * kAttnBlockKV, b);
+        tma_load_4d(sK + st * kAttnTileBytes, &tmap_k, &k_full[st], 0, j * kAttnBlockKV, h, b);
         mbar_expect_tx(&v_full[st], kAttnTileBytes);
-        tma_load_3d(sV + st * kAttnTileBytes, &tmap_v, &v_full[st], h * kAttnD, j * kAttnBlockKV, b);
+        tma_load_4d(sV + st * kAttnTileBytes, &tmap_v, &v_full[st], 0, j * kAttnBlockKV, h, b);
       }
     }
   } else if (warp == 1) {
@@ -238,7 +238,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     if (q0 + row < p.Tq) {
-      __nv_bfloat16* orow = p.O + (static_cast<size_t>(b) * p.Tq + q0 + row) * p.ldo + h * kAttnD;
+      __nv_bfloat16* orow = p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st;
 #pragma unroll
       for (int i = 0; i < kAttnD; i += 8) {
         uint4 o;
@@ -257,8 +257,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// 3-D map over a (B, T, cols) bf16 tensor with row pitch ld and batch pitch T*ld; box = [1, 128, 64].
-static int make_tmap_btc(CUtensorMap* out, const void* base, int B, int T, int cols, int ld) {
+// 4-D map over a bf16 tensor addressed as [b][h][t][d] with element strides (sb, sh, st, 1) and d = 64;
+// box = [1, 1, 128, 64].  Covers both (B, T, H*64) activations (sh = 64, st = row pitch) and the
+// reference's (B, H, T, D) layout (kernels/attention_fa2.py:113-140).  OOB rows (t >= T) read as zero.
+static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int T, long long sb, long long sh,
+                          long long st_) {
   typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -273,15 +276,16 @@ static int make_tmap_btc(CUtensorMap* out, const void* base, int B, int T, int c
     }
     fn = reinterpret_cast<Fn>(ptr);
   }
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
-  cuuint32_t box[3] = {64, 128, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  cuuint64_t dims[4] = {64, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)st_ * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(btc B=%d T=%d cols=%d ld=%d) failed: %d", B, T, cols, ld, (int)r);
+    set_error("cuTensorMapEncodeTiled(bhtd B=%d H=%d T=%d sb=%lld sh=%lld st=%lld) failed: %d", B, H, T, sb, sh, st_,
+              (int)r);
     return ST_ERR_CUDA;
   }
   return ST_OK;
@@ -293,22 +297,25 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 extern "C" {
 
-int st_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
-                      int H, int Tq, int Tk, float scale, st_stream_t stream) {
+int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q_st, const void* k, long long k_sb,
+                      long long k_sh, long long k_st, const void* v, long long v_sb, long long v_sh, long long v_st,
+                      void* o, long long o_sb, long long o_sh, long long o_st, int B, int H, int Tq, int Tk,
+                      float scale, st_stream_t stream) {
   using namespace st;
   ST_CHECK_ARG(q && k && v && o, "attention: null pointer");
   ST_CHECK_ARG(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: sizes must be positive");
-  ST_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: pitches must be multiples of 8");
-  ST_CHECK_ARG(ldq >= H * kAttnD && ldk >= H * kAttnD && ldv >= H * kAttnD && ldo >= H * kAttnD,
-               "attention: pitch smaller than H*64");
+  const long long strides[12] = {q_sb, q_sh, q_st, k_sb, k_sh, k_st, v_sb, v_sh, v_st, o_sb, o_sh, o_st};
+  for (int i = 0; i < 12; ++i)
+    ST_CHECK_ARG(strides[i] > 0 && strides[i] % 8 == 0, "attention: stride %d (%lld) must be a positive multiple of 8",
+                 i, strides[i]);
   ST_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "attention: pointers must be 16-byte aligned");
-  ST_CHECK_ARG(B * H <= 65535, "attention: B*H too large");
+  ST_CHECK_ARG((long long)B * H <= 65535, "attention: B*H too large");
   CUtensorMap tq, tk, tv;
-  int rc = make_tmap_btc(&tq, q, B, Tq, H * kAttnD, ldq);
+  int rc = make_tmap_bhtd(&tq, q, B, H, Tq, q_sb, q_sh, q_st);
   if (rc != ST_OK) return rc;
-  rc = make_tmap_btc(&tk, k, B, Tk, H * kAttnD, ldk);
+  rc = make_tmap_bhtd(&tk, k, B, H, Tk, k_sb, k_sh, k_st);
   if (rc != ST_OK) return rc;
-  rc = make_tmap_btc(&tv, v, B, Tk, H * kAttnD, ldv);
+  rc = make_tmap_bhtd(&tv, v, B, H, Tk, v_sb, v_sh, v_st);
   if (rc != ST_OK) return rc;
   static bool configured = false;
   if (!configured) {
@@ -321,7 +328,9 @@ int st_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void
   }
   AttnParams p;
   p.O = static_cast<__nv_bfloat16*>(o);
-  p.ldo = ldo;
+  p.o_sb = o_sb;
+  p.o_sh = o_sh;
+  p.o_st = o_st;
   p.H = H;
   p.Tq = Tq;
   p.Tk = Tk;

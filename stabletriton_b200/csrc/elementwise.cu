@@ -43,7 +43,7 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ state, int lds, c
 }
 
 // ---- tiny-M Linear: one warp per output column, all M rows at once ---------------------------------
-constexpr int kSmallMMax = 16;
+constexpr int kSmallMMax = 32;
 __global__ void __launch_bounds__(256)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
                       const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy, int M, int N,

@@ -322,12 +322,15 @@ static void test_attn_case(int B, int H, int Tq, int Tk, bool fused_qkv, bool ti
   CK(cudaMemset(o, 0xff, out * 2));
   CK(cudaMalloc(&oref, out * 4));
   const float scale = 0.125f;
-  ST(st_attention_bf16(q, ld, k, ld, v, ld, o, C, B, H, Tq, Tk, scale, 0));
+  ST(st_attention_bf16(q, (long long)Tq * ld, 64, ld, k, (long long)Tk * ld, 64, ld, v, (long long)Tk * ld, 64, ld, o,
+                       (long long)Tq * C, 64, C, B, H, Tq, Tk, scale, 0));
   CK(cudaDeviceSynchronize());
   ref_attention<<<dim3((Tq + 63) / 64, B * H), 64>>>(q, ld, k, ld, v, ld, oref, B, H, Tq, Tk, scale);
   CK(cudaDeviceSynchronize());
   float ms = -1;
-  if (timeit) ms = time_ms([&](cudaStream_t s) { st_attention_bf16(q, ld, k, ld, v, ld, o, C, B, H, Tq, Tk, scale, s); });
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_attention_bf16(q, (long long)Tq * ld, 64, ld, k, (long long)Tk * ld, 64, ld, v, (long long)Tk * ld, 64, ld, o,
+                        (long long)Tq * C, 64, C, B, H, Tq, Tk, scale, s);
+    });
   char name[128];
   snprintf(name, sizeof name, "attention B=%d H=%d Tq=%d Tk=%d fusedqkv=%d", B, H, Tq, Tk, fused_qkv);
   report(name, to_host(o, out), to_host_f(oref, out), 2e-2f, ms, 4.0 * B * H * (double)Tq * Tk * 64 * 1e-12,

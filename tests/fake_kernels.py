@@ -1,0 +1,110 @@
+"""Test double for `stabletriton_b200.kernels`: the same tensor-level API implemented with eager
+PyTorch, so the fx graph surgery can be validated on the CPU (no GPU in the build container).
+Test infrastructure only -- the product never imports this; on a GPU box the real kernels run.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+import stabletriton_b200.kernels as K
+
+CALLS: dict = {}
+
+
+def _count(name):
+    CALLS[name] = CALLS.get(name, 0) + 1
+
+
+def groupnorm_wrapper(input, num_groups, weight, bias, eps, activation=False):
+    _count("groupnorm")
+    y = F.group_norm(input, num_groups, weight, bias, eps)
+    return F.silu(y) if activation else y
+
+
+def layer_norm(x, weight, bias, eps):
+    _count("layer_norm")
+    return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+
+
+def linear(x, weight, bias=None, activation=False, residual=None, geglu=False, silu_input=False, block_n=0):
+    _count("linear_geglu" if geglu else "linear")
+    if silu_input:
+        x = F.silu(x)
+    y = F.linear(x, weight, bias)
+    if geglu:
+        s, g = y.chunk(2, dim=-1)
+        y = s * F.gelu(g)
+    if activation:
+        y = F.silu(y)
+    if residual is not None:
+        assert residual.shape == y.shape, (residual.shape, y.shape)
+        y = y + residual
+    return y
+
+
+def geglu_wrapper(state, gate):
+    _count("geglu")
+    return state * F.gelu(gate)
+
+
+def attention_btc(q, k, v, num_heads, sm_scale):
+    _count("attention")
+    b, t, c = q.shape
+    d = c // num_heads
+    qh = q.reshape(b, t, num_heads, d).transpose(1, 2)
+    kh = k.reshape(b, k.shape[1], num_heads, d).transpose(1, 2)
+    vh = v.reshape(b, v.shape[1], num_heads, d).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-2, -1) * sm_scale, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(b, t, c)
+
+
+def upsample_nearest2x(x):
+    _count("upsample")
+    return F.interpolate(x, scale_factor=2.0, mode="nearest")
+
+
+def conv2d(x, weight, bias, stride=1, padding=1, temb=None, residual=None, nchw_output=False, block_n=0):
+    _count("conv2d")
+    y = F.conv2d(x, weight, bias, stride=stride, padding=padding)
+    if temb is not None:
+        assert temb.shape == y.shape[:2]
+        y = y + temb[:, :, None, None]
+    if residual is not None:
+        assert residual.shape == y.shape
+        y = y + residual
+    return y
+
+
+def concat_channels(a, b):
+    _count("concat")
+    return torch.cat([a, b], dim=1)
+
+
+def timestep_embedding(t, num_channels):
+    _count("timestep")
+    import math
+    half = num_channels // 2
+    f = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    e = t.reshape(-1)[:, None].float() * f[None, :]
+    return torch.cat([torch.cos(e), torch.sin(e)], dim=-1)
+
+
+_NAMES = ["groupnorm_wrapper", "layer_norm", "linear", "geglu_wrapper", "attention_btc", "upsample_nearest2x",
+          "conv2d", "concat_channels", "timestep_embedding"]
+
+
+@contextlib.contextmanager
+def installed():
+    """Temporarily route `stabletriton_b200.kernels.*` to the eager implementations above."""
+    saved = {n: getattr(K, n) for n in _NAMES}
+    CALLS.clear()
+    try:
+        for n in _NAMES:
+            setattr(K, n, globals()[n])
+        yield CALLS
+    finally:
+        for n, f in saved.items():
+            setattr(K, n, f)
