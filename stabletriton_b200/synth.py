@@ -92,6 +92,21 @@ def synth_state_dict(module_on_meta: torch.nn.Module, seed: int = 0, device="cpu
     return sd
 
 
+def build_unet(cfg=None, seed: int = 0, device="cuda", dtype=torch.bfloat16):
+    """A `UNet2DConditionModel` with synthetic weights, built on the meta device (no default-init cost)
+    and materialised directly on `device`; values are generated in fp32 and rounded once to `dtype`."""
+    from .unet import UNet2DConditionModel, UNetConfig
+
+    cfg = cfg or UNetConfig.sdxl()
+    with torch.device("meta"):
+        model = UNet2DConditionModel(cfg)
+    sd = synth_state_dict(model, seed=seed, device=device, dtype=dtype)
+    model.load_state_dict(sd, strict=True, assign=True)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model.eval()
+
+
 def synth_inputs(batch: int, latent: int, cfg, seed: int = 1234, device="cpu", dtype=torch.float32,
                  timestep: float = 999.0):
     """UNet inputs of SURVEY section 8d: sample ~ U-hash scaled to unit variance, ctx (B, 77, ctx_dim),
