@@ -86,7 +86,8 @@ int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const
  * 143-182) and torch.nn.Conv2d at the sites unet_pt.py:58-60,64-66,260-262.
  * x: [N, H, W, C]; w: [K, 3, 3, C] (KRSC == channels-last Conv2d weight); y: [N, H, W, K].
  * y = conv(x, w) + bias[K] (+ temb[N, K] broadcast over pixels, unet_pt.py:82-83) (+ residual[N,H,W,K],
- * unet_pt.py:93).  Needs C % 64 == 0, K % 8 == 0, (H*W) % 128 == 0 and W in {16,32,64,128} or W % 128 == 0. */
+ * unet_pt.py:93).  Needs C % 64 == 0, K % 8 == 0 and either (H*W) % 128 == 0 with W dividing 128 or a multiple of it, or
+ * H*W dividing 128 (small feature maps: one tile covers several whole images). */
 int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int C, int K,
                          const void* temb, int ld_temb, const void* residual, unsigned flags, int block_n,
                          st_stream_t stream);

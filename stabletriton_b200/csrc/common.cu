@@ -75,7 +75,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t Ht,
-                   uint32_t Wt) {
+                   uint32_t Wt, uint32_t Nt) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -83,7 +83,7 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, u
   }
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {64, Wt, Ht, 1};
+  cuuint32_t box[4] = {64, Wt, Ht, Nt};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -20,9 +20,9 @@ unsigned long long* launch_counter();
 // box = [box_rows, 64 cols], 128-byte swizzle.  Returns 0 on success.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                  uint32_t box_cols = 64);
-// 4-D bf16 tensor map over an NHWC activation [N, H, W, C] (C contiguous); box = [1, Ht, Wt, 64].
+// 4-D bf16 tensor map over an NHWC activation [N, H, W, C] (C contiguous); box = [Nt, Ht, Wt, 64].
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t Ht,
-                   uint32_t Wt);
+                   uint32_t Wt, uint32_t Nt = 1);
 
 #define ST_CHECK_ARG(cond, ...)        \
   do {                                 \

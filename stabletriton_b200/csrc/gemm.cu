@@ -129,11 +129,21 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   ST_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && K > 0, "conv3x3: sizes must be positive");
   ST_CHECK_ARG(C % 64 == 0, "conv3x3: C (%d) must be a multiple of 64 (use st_conv3x3_direct_nhwc_bf16)", C);
   ST_CHECK_ARG(K % 8 == 0, "conv3x3: K (%d) must be a multiple of 8", K);
-  ST_CHECK_ARG((H * W) % kGemmBlockM == 0, "conv3x3: H*W (%d) must be a multiple of 128", H * W);
-  int Wt = W < 128 ? W : 128;
-  ST_CHECK_ARG(W % Wt == 0 && 128 % Wt == 0, "conv3x3: unsupported width %d", W);
-  const int Ht = 128 / Wt;
-  ST_CHECK_ARG(H % Ht == 0, "conv3x3: unsupported height %d for width %d", H, W);
+  // A tile = 128 output pixels = a Wt x Ht rectangle of one image, or Nt whole (small) images.
+  int Wt, Ht, Nt;
+  if (H * W >= kGemmBlockM) {
+    ST_CHECK_ARG((H * W) % kGemmBlockM == 0, "conv3x3: H*W (%d) must be a multiple of 128 (or divide 128)", H * W);
+    Wt = W < 128 ? W : 128;
+    ST_CHECK_ARG(W % Wt == 0 && 128 % Wt == 0, "conv3x3: unsupported width %d", W);
+    Ht = 128 / Wt;
+    Nt = 1;
+    ST_CHECK_ARG(H % Ht == 0, "conv3x3: unsupported height %d for width %d", H, W);
+  } else {
+    ST_CHECK_ARG(kGemmBlockM % (H * W) == 0, "conv3x3: H*W (%d) must divide 128 (or be a multiple of it)", H * W);
+    Wt = W;
+    Ht = H;
+    Nt = kGemmBlockM / (H * W);
+  }
   ST_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y), "conv3x3: pointers must be 16-byte aligned");
   ST_CHECK_ARG(!(flags & ST_EPI_GEGLU), "conv3x3: GEGLU epilogue not supported");
   ST_CHECK_ARG(!temb || (aligned16(temb) && ld_temb % 8 == 0), "conv3x3: bad temb pitch/alignment");
@@ -147,7 +157,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.K = 9 * C;
   p.n_out = K;
   p.ldd = K;
-  p.num_m_blocks = M / kGemmBlockM;
+  p.num_m_blocks = (M + kGemmBlockM - 1) / kGemmBlockM;
   p.num_n_blocks = (K + block_n - 1) / block_n;
   p.D = static_cast<__nv_bfloat16*>(y);
   p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -164,7 +174,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.conv_Ht = Ht;
 
   CUtensorMap ta, tb;
-  int rc = make_tmap_nhwc(&ta, x, N, H, W, C, Ht, Wt);
+  int rc = make_tmap_nhwc(&ta, x, N, H, W, C, Ht, Wt, Nt);
   if (rc != ST_OK) return rc;
   rc = make_tmap_2d(&tb, w, K, 9 * (uint64_t)C, 9 * (uint64_t)C, block_n);
   if (rc != ST_OK) return rc;

@@ -294,6 +294,8 @@ static void test_conv() {
   test_conv_case(1, 64, 64, 64, 320, false, true, 0, false);
   test_conv_case(1, 8, 128, 64, 64, true, true, 64, false);
   test_conv_case(1, 4, 256, 64, 64, false, false, 64, false);
+  test_conv_case(3, 8, 8, 64, 64, true, true, 64, false);
+  test_conv_case(1, 4, 4, 128, 64, true, false, 64, false);
   test_conv_case(2, 128, 128, 320, 320, true, false, 0, true);
   test_conv_case(2, 64, 64, 640, 640, false, true, 0, true);
   test_conv_case(2, 32, 32, 1280, 1280, true, false, 0, true);
