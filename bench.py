@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Contract benchmark: SDXL UNet denoise it/s at 1024^2, bf16, CFG batch 2 per prompt, CUDA graph.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one denoise iteration of the hot path for one prompt: scale_model_input -> UNet forward on
+the [uncond ; cond] pair (2, 4, 128, 128) -> guidance mix + Euler update, i.e. what the reference's tqdm
+bar counts as one "it" (README.md:1).  N > 1 (torchrun, one rank per GPU): weak scaling, every rank runs
+its own prompt with a full weight replica; value = N x steps / max-over-ranks time.  Images/s = it/s / 30.
+
+JSON line keys follow the driver contract; see DESIGN.md "Measurement".
+  value      steps/s with all inputs resident in HBM (step graph replays, device-side loop state)
+  e2e        same metric through the public API `compiled_unet(sample, t, ctx, added)` with pinned-host
+             inputs: H2D of that step's inputs + D2H of eps inside the timed region
+  roofline   dominant kernel = gemm_bf16_tc_kernel (all Linear / conv launches of the step): algorithmic
+             FLOPs of those launches / their device time, measured live by re-issuing exactly those
+             launches in a CUDA graph and timing it with CUDA events on the launching stream
+  cpu_baseline  the oracle port of the reference's eager fp32 UNet (oracle/unet_oracle.py) on the host
+             cores at BASELINE config 1 (B=1, 64x64 latent), scaled to the metric's unit by FLOPs
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SDXL UNet it/s at 1024^2 bf16 CFG"
+UNIT = "it/s"
+FLOPS_CONFIG2 = 13.522e12  # per CFG-batch-2 UNet forward at 1024^2
+FLOPS_CONFIG1 = 1.589e12   # B=1, 64x64 latent
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"],
+                "tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's eager path, on the host cores
+# ---------------------------------------------------------------------------------------------------
+def load_oracle():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("unet_oracle", os.path.join(ROOT, "oracle", "unet_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference_times(timed: int, warmup: int):
+    """Seconds per fp32 UNet forward of the oracle port at config 1 (B=1, 4x64x64), all host threads."""
+    import torch
+    from stabletriton_b200 import UNet2DConditionModel, UNetConfig, synth
+
+    cores = torch.get_num_threads()  # torch's default intra-op pool = all host cores
+    oracle = load_oracle()
+    cfg = UNetConfig.sdxl()
+    with torch.device("meta"):
+        meta = UNet2DConditionModel(cfg)
+    gen = torch.Generator().manual_seed(0)
+    sd = {}
+    for name, p in meta.state_dict().items():  # default-init-like scale, fast generator (timing only)
+        t = torch.empty(p.shape, dtype=torch.float32)
+        bound = 1.0 / max(1.0, (p.numel() / p.shape[0]) ** 0.5) if p.dim() > 1 else 0.02
+        t.uniform_(-bound, bound, generator=gen)
+        if name.endswith("weight") and "norm" in name:
+            t.mul_(0.1).add_(1.0)
+        sd[name] = t
+    inp = synth.synth_inputs(1, 64, cfg)
+    times = []
+    for i in range(warmup + timed):
+        t0 = time.perf_counter()
+        oracle.unet_forward(sd, inp["sample"], inp["timesteps"], inp["encoder_hidden_states"], inp["added_cond_kwargs"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    timed = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    times, cores = cpu_reference_times(timed, warm)
+    sec = statistics.median(times)
+    value = (1.0 / sec) * (FLOPS_CONFIG1 / FLOPS_CONFIG2)  # config-2-equivalent it/s, scaled by FLOPs
+    sample = (f"oracle port of reference eager fp32 UNet, B=1 4x64x64 (BASELINE config 1), {timed} timed forwards "
+              f"(median {sec:.2f} s each, {FLOPS_CONFIG1 / sec / 1e12:.3f} TFLOP/s), scaled to config 2 by FLOPs "
+              f"(x{FLOPS_CONFIG1 / FLOPS_CONFIG2:.4f})")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+        "warmup": warm, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SDXL UNet denoise step, 1024^2, CFG batch 2 (CPU arm timed at config 1 and scaled)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.file.read().splitlines():
+            cols = [c.strip() for c in row.split(",")]
+            if len(cols) < 9:
+                continue
+            try:
+                sm.append(float(cols[1]))
+                mx = float(cols[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, cols[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.file.name)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def gemm_family_flops(calls):
+    flops = 0.0
+    for name, a in calls:
+        if name == "st_gemm_bf16":
+            flops += 2.0 * a[6] * a[7] * a[8]
+        elif name == "st_conv3x3_nhwc_bf16":
+            n, h, w, c, k = a[4:9]
+            flops += 2.0 * n * h * w * k * c * 9
+    return flops
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import stabletriton_b200 as st
+    from stabletriton_b200 import UNetConfig, _cabi, synth
+    from stabletriton_b200.build import build
+    from stabletriton_b200.pipeline import DenoiseLoop
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    if not os.path.exists(_cabi.LIB_PATH):
+        build(selftest=False)
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    cfg = UNetConfig.sdxl()
+    latent, prompts = args.latent, args.prompts
+    model = synth.build_unet(cfg, seed=7, device=device)
+    compiled = st.compile(model, cuda_graph=True)
+
+    # ---- resident-input arm: step graph (UNet + scheduler) ---------------------------------------
+    loop = DenoiseLoop(compiled, prompts=prompts, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device)
+    inp = synth.synth_inputs(prompts, latent, cfg, seed=1234 + rank, device=device, dtype=torch.bfloat16)
+    cond = {"encoder_hidden_states": inp["encoder_hidden_states"], **inp["added_cond_kwargs"]}
+    unc = synth.synth_inputs(prompts, latent, cfg, seed=4321 + rank, device=device, dtype=torch.bfloat16)
+    uncond = {"encoder_hidden_states": unc["encoder_hidden_states"], **unc["added_cond_kwargs"]}
+    loop.set_conditioning(cond, uncond)
+    loop.reset(inp["sample"].float())
+    before = _cabi.launch_count()
+    loop.capture()
+    launches_per_step = (_cabi.launch_count() - before) // 3  # 2 warm-up bodies + 1 captured body
+    loop.reset(inp["sample"].float())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(warmup):
+        loop.run_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        loop.run_step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+
+    # ---- e2e arm: public API, pinned-host inputs, H2D + D2H inside the timed region ----------------
+    b2 = synth.synth_inputs(2 * prompts, latent, cfg, seed=99 + rank, device="cpu", dtype=torch.bfloat16)
+    host = {
+        "sample": b2["sample"].pin_memory(), "t": torch.tensor(999.0).pin_memory(),
+        "ctx": b2["encoder_hidden_states"].pin_memory(),
+        "text": b2["added_cond_kwargs"]["text_embeds"].pin_memory(),
+        "ids": b2["added_cond_kwargs"]["time_ids"].pin_memory(),
+    }
+    eps_host = torch.empty((2 * prompts, cfg.out_channels, latent, latent), dtype=torch.bfloat16).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = eps_host.numel() * eps_host.element_size()
+
+    def e2e_step():
+        s = host["sample"].to(device, non_blocking=True)
+        t = host["t"].to(device, non_blocking=True)
+        c = host["ctx"].to(device, non_blocking=True)
+        added = {"text_embeds": host["text"].to(device, non_blocking=True),
+                 "time_ids": host["ids"].to(device, non_blocking=True)}
+        eps = compiled(s, t, c, added)[0]
+        eps_host.copy_(eps, non_blocking=True)
+
+    for _ in range(warmup):
+        e2e_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- max over ranks -------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- roofline of the dominant kernel family, measured live ----------------------------------------
+        keep = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device)
+        b = synth.synth_inputs(2 * prompts, latent, cfg, seed=5, device=device, dtype=torch.bfloat16)
+        with torch.no_grad(), torch.cuda.stream(side):
+            with torch.cuda.graph(keep, stream=side):
+                _cabi.start_recording()
+                compiled.eager_forward(b["sample"], b["timesteps"], b["encoder_hidden_states"], b["added_cond_kwargs"])
+                calls = _cabi.stop_recording()
+        gemm_calls = [c for c in calls if c[0] in ("st_gemm_bf16", "st_conv3x3_nhwc_bf16")]
+        fam = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            _cabi.replay(gemm_calls, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize(device)
+            with torch.cuda.graph(fam, stream=side):
+                _cabi.replay(gemm_calls, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize(device)
+        for _ in range(3):
+            fam.replay()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        f0.record()
+        for _ in range(reps):
+            fam.replay()
+        f1.record()
+        torch.cuda.synchronize(device)
+        fam_ms = f0.elapsed_time(f1) / reps
+        fam_flops = gemm_family_flops(gemm_calls)
+        achieved = fam_flops / (fam_ms * 1e-3) / 1e12
+        ms_step = ms_total / steps
+        roofline = {
+            "bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all Linear + conv launches of one step)",
+            "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+            "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "launches_per_step": len(gemm_calls),
+            "flops_per_step": fam_flops, "ms_per_step_in_kernel": fam_ms, "share_of_step": fam_ms / ms_step,
+            "whole_step_frac_of_roofline": (FLOPS_CONFIG2 * prompts / peaks["tflops_sustained"] / 1e12
+                                            + 3.754e9 * prompts / peaks["hbm_gbs"] / 1e9) / (ms_step * 1e-3),
+        }
+        # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
+        cpu = None
+        if not args.no_cpu_baseline:
+            times, cores = cpu_reference_times(timed=2, warmup=1)
+            sec = statistics.median(times)
+            cpu = {
+                "value": (1.0 / sec) * (FLOPS_CONFIG1 / FLOPS_CONFIG2), "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": (f"oracle port of the reference eager fp32 UNet at BASELINE config 1 (B=1, 4x64x64), 2 timed "
+                           f"forwards, median {sec:.2f} s ({FLOPS_CONFIG1 / sec / 1e12:.3f} TFLOP/s), scaled to "
+                           f"config 2 by FLOPs"),
+            }
+        value = world * prompts * steps / (ms_total * 1e-3)
+        e2e_value = world * prompts * steps / (ms_e2e * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": f"SDXL UNet denoise step, {latent * 8}^2, CFG batch 2 x {prompts} prompt(s) per GPU, "
+                            f"Euler + guidance 5.0, CUDA graph (BASELINE configs[1])",
+                "prompts_per_gpu": prompts, "latent": latent, "parallelism": f"dp{world}",
+                "l2": "no explicit flush: every step streams 5.1 GB of bf16 weights (> 126 MB L2)",
+                "weights": "random-init (hash-seeded), Diffusers SDXL-base architecture, 2.567 B params",
+            },
+            "images_per_s_30_steps": value / 30.0,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches_per_step) * steps,
+            "launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--latent", type=int, default=128, help="latent side (128 = 1024^2)")
+    ap.add_argument("--prompts", type=int, default=1, help="prompts per GPU (each is a CFG pair)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
