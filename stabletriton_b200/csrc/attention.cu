@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kAttnTileBytes;
   uint8_t* sV = sK + kAttnStages * kAttnTileBytes;

@@ -4,25 +4,28 @@
 
 namespace st {
 
-// Pick the B-tile width that minimises (waves x per-tile cost) on this device.  Tiles are 128 rows
-// tall; the per-tile cost model is (BLOCK_N + fixed overhead) -- MMA time scales with BLOCK_N, the
-// overhead term stands for pipeline fill and the non-overlapped part of the epilogue.
+// Pick the B-tile width.  Measured cost model (profiles/r01_gemm_trace.txt): a 128 x BLOCK_N x 64
+// k-block costs ~512 cycles of tensor pipe whatever BLOCK_N <= 256 is (SS-mode A-read bound), the
+// epilogue costs a few cycles per output column, and tiles are spread over the SMs in waves.  So the
+// widest tile that does not add a wave wins; ties go to the narrower tile (less operand traffic).
 static int choose_block_n(int M, int n_cols, bool geglu, int K) {
   const int sms = device_sm_count();
   const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-  const int cands[3] = {256, 128, 64};
-  int best = 128;
+  const int cands_plain[4] = {64, 128, 192, 256};
+  const int cands_geglu[2] = {128, 256};
+  const int* cands = geglu ? cands_geglu : cands_plain;
+  const int ncand = geglu ? 2 : 4;
+  int best = 256;
   double best_cost = 1e30;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < ncand; ++i) {
     const int bn = cands[i];
     const int out_cols = geglu ? bn / 2 : bn;
     const int nb = (n_cols + out_cols - 1) / out_cols;
     const long tiles = (long)mb * nb;
     const long waves = (tiles + sms - 1) / sms;
-    // per-tile: MMA cycles ~ bn * K/64 * (64/16) * ... proportional to bn*K; epilogue ~ out_cols; fill ~ const
-    const double tile_cost = (double)bn * K / 64.0 + 0.6 * bn + 24.0;
+    const double tile_cost = 512.0 * (K / 64) + 1500.0 + 10.0 * out_cols;
     const double cost = waves * tile_cost;
-    if (cost < best_cost * 0.999) {
+    if (cost < best_cost * 0.97) {
       best_cost = cost;
       best = bn;
     }
@@ -31,7 +34,8 @@ static int choose_block_n(int M, int n_cols, bool geglu, int K) {
 }
 
 template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
+                       cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES>;
   auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu>;
   static bool configured = false;  // per instantiation
@@ -45,30 +49,32 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kernel<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, p);
+  kernel<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, td, p);
   ST_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return ST_OK;
 }
 
 template <bool kConvA>
-static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int block_n, bool geglu,
-                         cudaStream_t stream) {
+static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
+                         int block_n, bool geglu, cudaStream_t stream) {
   if (geglu) {
     switch (block_n) {
-      case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, p, stream);
-      case 128: return launch_gemm<128, 6, kConvA, true>(ta, tb, p, stream);
-      case 64: return launch_gemm<64, 8, kConvA, true>(ta, tb, p, stream);
+      case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, td, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, true>(ta, tb, td, p, stream);
     }
   } else {
     switch (block_n) {
-      case 256: return launch_gemm<256, 4, kConvA, false>(ta, tb, p, stream);
-      case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, p, stream);
-      case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, p, stream);
+      case 256: return launch_gemm<256, 4, kConvA, false>(ta, tb, td, p, stream);
+      case 192: return launch_gemm<192, 5, kConvA, false>(ta, tb, td, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, td, p, stream);
+      case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, td, p, stream);
     }
   }
-  set_error("gemm: unsupported block_n %d (use 0, 64, 128 or 256)", block_n);
+  set_error("gemm: unsupported block_n %d (use 0, 128 or 256; 64 and 192 without GEGLU)", block_n);
   return ST_ERR_INVALID_ARGUMENT;
 }
+
+static unsigned long long* g_gemm_trace = nullptr;  // debug only, see st_debug_set_gemm_trace
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -112,13 +118,17 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.rowbias = nullptr;
   p.rows_per_batch = 1;
   p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
+  p.trace = g_gemm_trace;
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, M, K, lda, kGemmBlockM);
   if (rc != ST_OK) return rc;
   rc = make_tmap_2d(&tb, W, N, K, ldw, geglu ? block_n / 2 : block_n);
   if (rc != ST_OK) return rc;
-  return dispatch_gemm<false>(ta, tb, p, block_n, geglu, static_cast<cudaStream_t>(stream));
+  CUtensorMap td;
+  rc = make_tmap_2d(&td, D, M, n_out, ldd, kGemmBlockM);
+  if (rc != ST_OK) return rc;
+  return dispatch_gemm<false>(ta, tb, td, p, block_n, geglu, static_cast<cudaStream_t>(stream));
 }
 
 int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int C, int K,
@@ -167,6 +177,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.ld_rowbias = ld_temb;
   p.rows_per_batch = H * W;
   p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
+  p.trace = g_gemm_trace;
   p.conv_H = H;
   p.conv_W = W;
   p.conv_C = C;
@@ -178,7 +189,14 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   if (rc != ST_OK) return rc;
   rc = make_tmap_2d(&tb, w, K, 9 * (uint64_t)C, 9 * (uint64_t)C, block_n);
   if (rc != ST_OK) return rc;
-  return dispatch_gemm<true>(ta, tb, p, block_n, false, static_cast<cudaStream_t>(stream));
+  CUtensorMap td;
+  rc = make_tmap_2d(&td, y, M, K, K, kGemmBlockM);
+  if (rc != ST_OK) return rc;
+  return dispatch_gemm<true>(ta, tb, td, p, block_n, false, static_cast<cudaStream_t>(stream));
 }
+
+// Debug hook (not part of the product surface): when set, every GEMM/conv CTA writes 8 clock64 stamps
+// (start, setup done, first operands landed, MMA issue done, accumulator ready, epilogue done, exit) to buf.
+void st_debug_set_gemm_trace(void* buf) { st::g_gemm_trace = static_cast<unsigned long long*>(buf); }
 
 }  // extern "C"

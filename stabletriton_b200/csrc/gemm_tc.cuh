@@ -2,11 +2,20 @@
 //
 //   D[m, n] = epilogue( sum_k A[m, k] * B[n, k] )        A, B bf16 (K contiguous), fp32 accumulate in TMEM
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer (one elected
-// lane), warps 2..5 = epilogue (TMEM -> registers -> bias / SiLU / GEGLU / residual -> bf16 -> HBM).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer (one elected
+// lane), warps 2..9 = epilogue (TMEM -> registers -> bias / SiLU / GEGLU / residual -> bf16 -> HBM).
 // Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), two TMEM accumulator stages
 // (tmem_full/tmem_empty, MMA <-> epilogue) and a static persistent tile schedule (tile = blockIdx.x +
 // i * gridDim.x), so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Measured on B200 (profiles/r01_gemm_trace.txt): with both operands in shared memory a
+// 128 x N x 16 tcgen05.mma costs ~128 cycles for every N <= 256 (the 4 KB A-slice read bounds it), so
+// only wide tiles reach the tensor peak -- the launcher prefers BLOCK_N = 256.  The epilogue therefore
+// has to stay off the critical path: the per-tile bias (+ per-image time-embedding row) is staged
+// once in shared memory, the residual rows are prefetched into registers *before* the accumulator is
+// waited for, and the bf16 result leaves through a swizzled staging tile and TMA bulk stores
+// (64 columns x 128 rows each, clipped at the matrix edge by the tensor map), so no global-memory
+// round trip and no uncoalesced store sits between TMEM and HBM.
 //
 // A is fetched either through a 2-D tensor map (plain GEMM: Linear, 1x1 conv, im2col'ed conv) or a
 // 4-D NHWC tensor map (3x3 / pad 1 / stride 1 convolution): the 128 output pixels of a tile form a
@@ -22,7 +31,8 @@ namespace st {
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmEpiThreads = 256;              // 8 epilogue warps
+constexpr int kGemmThreads = 64 + kGemmEpiThreads;  // + TMA producer warp + MMA issuer warp
 
 struct GemmParams {
   int M, N, K;          // N = number of B rows consumed (for GEGLU: 2 * n_out), K = reduction length
@@ -37,6 +47,7 @@ struct GemmParams {
   int ld_rowbias;
   int rows_per_batch;
   int act_silu;  // apply SiLU after bias
+  unsigned long long* trace;  // debug: 8 clock64 stamps per CTA (see ST_TRACE), or nullptr
   // 4-D (conv) A addressing
   int conv_H, conv_W, conv_C;  // input == output spatial size (3x3, pad 1, stride 1)
   int conv_Wt, conv_Ht;        // tile rectangle, Wt * Ht == 128
@@ -47,47 +58,71 @@ struct GemmSmem {
   static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutStageBytes = kGemmBlockM * 64 * 2;  // epilogue staging tile for the TMA store
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kBiasBytes = 2 * BLOCK_N * 4;  // two accumulator stages x BLOCK_N fp32
+  static constexpr int kTotal =
+      STAGES * kStageBytes + kOutStageBytes + kBarrierBytes + kBiasBytes + 1024;  // +1024: alignment slack
 };
 
-__host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+__host__ __device__ constexpr int tmem_cols_for(int n) {
+  return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
+}
+
+__device__ __forceinline__ void add_bf16x8(float (&x)[8], const uint4& u) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16x2(w[e]);
+    x[2 * e] += f.x;
+    x[2 * e + 1] += f.y;
+  }
+}
 
 // kConvA: A through the 4-D NHWC map.  kGeglu: B tile = [BLOCK_N/2 "state" rows | BLOCK_N/2 "gate" rows].
 template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
   using S = GemmSmem<BLOCK_N, STAGES>;
   constexpr int kAccCols = BLOCK_N;                       // fp32 accumulator columns per stage
   constexpr int kTmemCols = tmem_cols_for(2 * kAccCols);  // two accumulator stages
   static_assert(2 * kAccCols <= 512, "accumulator stages exceed TMEM");
-  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+  static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "BLOCK_N");
+  static_assert(!kGeglu || BLOCK_N % 128 == 0, "the TMA store works on 64-column groups of the output tile");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_ab = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStageBytes);
+  uint8_t* s_out = smem + STAGES * S::kStageBytes;  // 1024-byte aligned: stages are multiples of 8 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_out + S::kOutStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(s_out + S::kOutStageBytes + S::kBarrierBytes);  // [2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_k_blocks = p.K / kGemmBlockK;
+#define ST_TRACE(slot)                                                      \
+  do {                                                                      \
+    if (p.trace) p.trace[blockIdx.x * 12 + (slot)] = clock64();              \
+  } while (0)
+  if (threadIdx.x == 0) ST_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_d);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kGemmEpiThreads / 32);
     }
     mbar_fence_init();
   }
@@ -96,6 +131,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ST_TRACE(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -157,6 +193,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (tile == blockIdx.x && kb == 0) ST_TRACE(2);
           const uint32_t a_addr = smem_u32(smem_ab + stage * S::kStageBytes);
           const uint32_t b_addr = a_addr + S::kABytes;
 #pragma unroll
@@ -172,6 +209,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (tile == blockIdx.x) ST_TRACE(3);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -180,113 +218,169 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================================== epilogue =========================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // 8 warps: warp w may touch TMEM lane quadrant (w & 3); the two warps of a quadrant split every
+    // 64-column group of the tile (columns 0-31 / 32-63), which doubles the number of independent
+    // instruction streams per scheduler -- one warp per scheduler leaves the dependent FADD/convert/
+    // pack chain latency-bound (measured: ~1000 cycles per 32-column chunk).
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;        // 0: columns [0,32) of each group, 1: columns [32,64)
+    const int etid = threadIdx.x - 64;       // 0..255 among the epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int kOutCols = kGeglu ? BLOCK_N / 2 : BLOCK_N;
+    constexpr int kGroups = kOutCols / 64;   // 64-column groups = TMA store boxes
+    // the time-embedding row can be folded into the staged bias when a tile lies inside one image
+    const bool rowbias_per_tile = p.rowbias != nullptr && p.rows_per_batch >= kGemmBlockM;
+    const bool rowbias_per_row = p.rowbias != nullptr && !rowbias_per_tile;
+    const int tile_row = quad * 32 + lane;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % p.num_m_blocks;
       const int n_blk = tile / p.num_m_blocks;
-      const int row = m_blk * kGemmBlockM + quad * 32 + lane;
+      const int row = m_blk * kGemmBlockM + tile_row;
       const int n0 = n_blk * kOutCols;
+      const bool row_ok = row < p.M;
+      float* sb = s_bias + acc * BLOCK_N;
+
+      // (1) stage this tile's bias (+ per-image row bias) as fp32: sb[0..kOutCols) state / plain,
+      //     sb[kOutCols..2*kOutCols) gate.  Buffer `acc` was last read two tiles ago by these same threads.
+      {
+        const __nv_bfloat16* rb =
+            rowbias_per_tile ? p.rowbias + static_cast<size_t>((m_blk * kGemmBlockM) / p.rows_per_batch) * p.ld_rowbias
+                             : nullptr;
+        for (int c = etid; c < BLOCK_N; c += kGemmEpiThreads) {
+          const int hb = kGeglu ? c / kOutCols : 0;
+          const int col = n0 + (kGeglu ? c - hb * kOutCols : c);
+          float b = 0.f;
+          if (col < p.n_out) {
+            if (p.bias) b = __bfloat162float(p.bias[hb * p.n_out + col]);
+            if (rb) b += __bfloat162float(rb[col]);
+          }
+          sb[c] = b;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+
+      // (2) prefetch this thread's residual columns into registers while the main loop is still running
+      uint4 res[kGroups * 4];
+      const bool has_res = p.residual != nullptr && row_ok;
+      if (has_res) {
+        const __nv_bfloat16* res_row = p.residual + static_cast<size_t>(row) * p.ldr + n0 + half * 32;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g)
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (n0 + g * 64 + half * 32 + v * 8 < p.n_out) res[g * 4 + v] = ld_global_nc_v4_early(res_row + g * 64 + v * 8);
+      }
+      const __nv_bfloat16* rb_row =
+          rowbias_per_row ? p.rowbias + static_cast<size_t>(row_ok ? row / p.rows_per_batch : 0) * p.ld_rowbias : nullptr;
+
+      // (3) accumulator ready
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(4);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
-      const bool row_ok = row < p.M;
-      const __nv_bfloat16* res_row = p.residual ? p.residual + static_cast<size_t>(row) * p.ldr : nullptr;
-      const __nv_bfloat16* rb_row =
-          p.rowbias ? p.rowbias + static_cast<size_t>(row_ok ? row / p.rows_per_batch : 0) * p.ld_rowbias : nullptr;
-      __nv_bfloat16* d_row = p.D + static_cast<size_t>(row) * p.ldd;
-#pragma unroll 1
-      for (int c = 0; c < kOutCols; c += 32) {
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        if (n0 + g * 64 >= p.n_out) break;  // this 64-column group lies entirely past the matrix edge
+        const int c = g * 64 + half * 32;   // first tile column of this thread's chunk
         uint32_t v[32];
-        uint32_t g[32];
+        uint32_t gt[32];
         tmem_ld_32x32b_x32(t_row + c, v);
-        if (kGeglu) tmem_ld_32x32b_x32(t_row + BLOCK_N / 2 + c, g);
+        if (kGeglu) tmem_ld_32x32b_x32(t_row + kOutCols + c, gt);
         tmem_ld_wait();
-        if (row_ok) {
+        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(7);
+        // the staging tile is reused per group: wait until the previous TMA store has read it
+        if (etid == 0) tma_store_wait_read();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(8);
+        // All shared-memory reads of this chunk first (the compiler cannot hoist them over the staging
+        // stores below: both live in shared memory), then straight-line register math on 32 columns.
+        float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = n0 + c + j;
-            if (col < p.n_out) {  // n_out is a multiple of 8 (checked on the host)
-              float x[8];
+        for (int q = 0; q < 8; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(sb + c + 4 * q);
+          x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
+          x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
+          x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
+          x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+        }
+        if (kGeglu) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j + e]);
-              if (p.bias) {
-                const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16x2(bw[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
-                }
-              }
-              if (kGeglu) {
-                float gt[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) gt[e] = __uint_as_float(g[j + e]);
-                if (p.bias) {
-                  const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + p.n_out + col);
-                  const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = unpack_bf16x2(bw[e]);
-                    gt[2 * e] += f.x;
-                    gt[2 * e + 1] += f.y;
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
-              }
-              if (rb_row) {
-                const uint4 bv = *reinterpret_cast<const uint4*>(rb_row + col);
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16x2(bw[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
-                }
-              }
-              if (p.act_silu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
-              }
-              if (res_row) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res_row + col);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16x2(rw[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16x2(x[0], x[1]);
-              o.y = pack_bf16x2(x[2], x[3]);
-              o.z = pack_bf16x2(x[4], x[5]);
-              o.w = pack_bf16x2(x[6], x[7]);
-              *reinterpret_cast<uint4*>(d_row + col) = o;
-            }
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(sb + kOutCols + c + 4 * q);
+            x[4 * q + 0] *= gelu_erf_f(__uint_as_float(gt[4 * q + 0]) + b.x);
+            x[4 * q + 1] *= gelu_erf_f(__uint_as_float(gt[4 * q + 1]) + b.y);
+            x[4 * q + 2] *= gelu_erf_f(__uint_as_float(gt[4 * q + 2]) + b.z);
+            x[4 * q + 3] *= gelu_erf_f(__uint_as_float(gt[4 * q + 3]) + b.w);
           }
         }
+        if (rb_row) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (n0 + c + j < p.n_out) {
+              float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              add_bf16x8(t, *reinterpret_cast<const uint4*>(rb_row + n0 + c + j));
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[j + e] += t[e];
+            }
+        }
+        if (p.act_silu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) x[e] = silu_f(x[e]);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (n0 + c + j < p.n_out) {
+              const uint4 r4 = res[g * 4 + j / 8];
+              const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w[e]);
+                x[j + 2 * e] += f.x;
+                x[j + 2 * e + 1] += f.y;
+              }
+            }
+        }
+        // staging tile: [128 rows][64 cols] bf16, 128-byte swizzle (16-byte chunk ^= row & 7)
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          o.x = pack_bf16x2(x[j + 0], x[j + 1]);
+          o.y = pack_bf16x2(x[j + 2], x[j + 3]);
+          o.z = pack_bf16x2(x[j + 4], x[j + 5]);
+          o.w = pack_bf16x2(x[j + 6], x[j + 7]);
+          const int chunk = half * 4 + (j >> 3);
+          *reinterpret_cast<uint4*>(s_out + tile_row * 128 + ((chunk ^ (tile_row & 7)) << 4)) = o;
+        }
+        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(9);
+        // 64 columns staged: hand them to the TMA store engine (clips rows >= M and columns >= n_out)
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (etid == 0) {
+          tma_store_2d(&tmap_d, s_out, n0 + g * 64, m_blk * kGemmBlockM);
+          tma_store_commit();
+        }
+        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(11);
       }
       tc_fence_before();
       __syncwarp();
+      if (tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(5);
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (etid == 0) tma_store_wait_all();  // smem must outlive the last bulk store
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  if (threadIdx.x == 0) ST_TRACE(6);
+#undef ST_TRACE
 }
 
 }  // namespace st

@@ -190,6 +190,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16-byte read-only global load that the compiler may not sink to its use site (asm volatile keeps
+// program order relative to the mbarrier waits): used to prefetch epilogue operands under the main loop.
+__device__ __forceinline__ uint4 ld_global_nc_v4_early(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// 1024-byte aligned start of the dynamic shared memory window, computed with pointer arithmetic on the
+// __shared__ array itself so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST).
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* base) {
+  return base + ((1024u - (smem_u32(base) & 1023u)) & 1023u);
+}
+
 // ------------------------------------------------------------------------------------------------
 // small numeric helpers
 // ------------------------------------------------------------------------------------------------
@@ -206,7 +219,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with the fast (MUFU.RCP) division: the IEEE-exact '/' costs a slow-path call per element
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 }  // namespace st

@@ -14,6 +14,7 @@
 
 #include "../../include/stabletriton_b200.h"
 
+extern "C" void st_debug_set_gemm_trace(void* buf);
 extern "C" int st_conv3x3_direct_bf16(const void*, long long, long long, long long, long long, const void*,
                                       const void*, void*, long long, long long, long long, long long, int, int, int,
                                       int, int, st_stream_t);
@@ -240,6 +241,8 @@ static void test_gemm() {
   test_gemm_case(384, 320, 320, ST_EPI_SILU, true, false, 0, false);
   test_gemm_case(300, 200, 192, 0, true, true, 128, false);    // ragged M and N, residual
   test_gemm_case(256, 512, 128, ST_EPI_GEGLU, true, false, 128, false);
+  test_gemm_case(300, 328, 192, 0, true, true, 192, false);
+  test_gemm_case(130, 72, 64, ST_EPI_SILU, true, true, 64, false);
   test_gemm_case(256, 1280, 320, ST_EPI_GEGLU, true, false, 256, false);
   // SDXL shapes, timed
   test_gemm_case(2048, 1280, 1280, 0, true, true, 0, true);
@@ -645,6 +648,60 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s, sm_%d%d, %d SMs, lib version %d\n", prop.name, prop.major, prop.minor,
          prop.multiProcessorCount, st_version());
+  if (!strcmp(what, "trace") && argc >= 7) {  // selftest trace M N K flags block_n : per-CTA phase timeline
+    const int M = atoi(argv[2]), N = atoi(argv[3]), K = atoi(argv[4]);
+    const unsigned flags = (unsigned)atoi(argv[5]);
+    const int bn = atoi(argv[6]);
+    const int n_out = (flags & ST_EPI_GEGLU) ? N / 2 : N;
+    __nv_bfloat16* A = dev_bf16((size_t)M * K, 1.0f);
+    __nv_bfloat16* W = dev_bf16((size_t)N * K, 0.05f);
+    __nv_bfloat16* b = dev_bf16(N, 0.5f);
+    __nv_bfloat16* r = dev_bf16((size_t)M * n_out, 1.0f);
+    __nv_bfloat16* D;
+    CK(cudaMalloc(&D, (size_t)M * n_out * 2));
+    unsigned long long* tr;
+    CK(cudaMalloc(&tr, 148 * 12 * 8));
+    for (int it = 0; it < 3; ++it) ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, bn, 0));
+    CK(cudaMemset(tr, 0, 148 * 12 * 8));
+    st_debug_set_gemm_trace(tr);
+    ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, bn, 0));
+    CK(cudaDeviceSynchronize());
+    st_debug_set_gemm_trace(nullptr);
+    std::vector<unsigned long long> h(148 * 12);
+    CK(cudaMemcpy(h.data(), tr, 148 * 12 * 8, cudaMemcpyDeviceToHost));
+    const char* names[11] = {"setup", "first operands landed", "MMA issue done (tile 0)", "accumulator ready",
+                             "epilogue tile 0 done", "exit", "epi: chunk0 tmem ld done", "epi: chunk0 staging free",
+                             "epi: chunk0 math+sts done", "epi: chunk1 math+sts done", "epi: group0 store issued"};
+    for (int e = 1; e <= 11; ++e) {
+      double sum = 0, mn = 1e18, mx = 0;
+      int cnt = 0;
+      for (int c = 0; c < 148; ++c) {
+        if (!h[c * 12] || !h[c * 12 + e]) continue;
+        const double d = (double)(h[c * 12 + e] - h[c * 12]);
+        sum += d;
+        mn = d < mn ? d : mn;
+        mx = d > mx ? d : mx;
+        ++cnt;
+      }
+      printf("  t[%d] %-26s cycles since CTA start: min %8.0f avg %8.0f max %8.0f (n=%d)\n", e, names[e - 1], mn,
+             cnt ? sum / cnt : 0, mx, cnt);
+    }
+    return 0;
+  }
+  if (!strcmp(what, "gemm1") && argc >= 7) {  // selftest gemm1 M N K flags block_n [bias res]: one timed case (ncu target)
+    test_gemm_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), (unsigned)atoi(argv[5]), argc > 7 ? atoi(argv[7]) : 1,
+                   argc > 8 ? atoi(argv[8]) : 1, atoi(argv[6]), true);
+    return g_fail ? 1 : 0;
+  }
+  if (!strcmp(what, "conv1") && argc >= 8) {  // selftest conv1 N H W C K block_n
+    test_conv_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), true, false,
+                   atoi(argv[7]), true);
+    return g_fail ? 1 : 0;
+  }
+  if (!strcmp(what, "attn1") && argc >= 6) {  // selftest attn1 B H Tq Tk
+    test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, true);
+    return g_fail ? 1 : 0;
+  }
   const bool all = !strcmp(what, "all");
   if (all || !strcmp(what, "gemm")) test_gemm();
   if (all || !strcmp(what, "conv")) test_conv();
