@@ -1,12 +1,17 @@
-// Flash attention forward for head_dim 64 on sm_100a: TMA-fed tcgen05 tiles, S and the per-block
-// P.V product in TMEM, online softmax in fp32 registers (one thread per query row, so row max / sum
-// need no shuffles), P re-staged to 128B-swizzled shared memory as the A operand of the second MMA.
+// Flash attention forward for head_dim 64 on sm_100a: TMA-fed tcgen05 tiles, S, P and the per-block
+// P.V product all in TMEM, online softmax in fp32 registers (one thread per query row, so row max /
+// sum need no shuffles).
 //
 //   grid = (ceil(Tq / 128), B * H); 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-//   warps 2..5 softmax / accumulate / store.
-//   Pipelines: K/V smem ring (k_full, v_full, kv_empty), two S buffers (s_full) and two P buffers
-//   (p_full) so QK^T of block j+1 runs under the softmax of block j, two PV buffers (o_full, o_empty)
-//   whose result is folded into the register accumulator one block late.
+//   warps 2..5 softmax / accumulate / store.  Two CTAs are resident per SM (<= 82 KB smem, 256 TMEM
+//   columns, <= 168 registers), so while one CTA's softmax warps sit on the MUFU pipe the other CTA's
+//   MMAs keep the tensor pipe busy.
+//
+//   S = Q K^T        : tcgen05.mma SS (Q, K 128B-swizzled K-major tiles from TMA), 128 fp32 columns
+//   P = 2^(S*c - m)  : written back to TMEM as packed bf16 (64 columns) with tcgen05.st
+//   O_j = P V        : tcgen05.mma TS -- A operand straight from TMEM, V as an MN-major smem operand --
+//                      ~4x cheaper than the SS form (a 128x64x16 SS MMA is bound by the smem A fetch)
+//   O += O_j         : folded into fp32 registers one block late, rescaled by 2^(m_old - m_new)
 //
 // Semantics = the *pattern* of fuse_attention (reference: optimizers/replace_attention.py:76-86;
 // fp32 restatement ref_attention :109-124): per head softmax(Q K^T * scale) V, no mask, separate
@@ -20,19 +25,23 @@ namespace st {
 constexpr int kAttnBlockQ = 128;
 constexpr int kAttnBlockKV = 128;
 constexpr int kAttnD = 64;
-constexpr int kAttnStages = 3;
+constexpr int kAttnStages = 2;
 constexpr int kAttnThreads = 192;
 constexpr int kAttnTileBytes = 128 * 64 * 2;  // any [128 x 64] bf16 tile
-constexpr int kAttnSmemBytes = kAttnTileBytes * (1 + 2 * kAttnStages + 4) + 1024 + 1024;
+constexpr int kAttnSmemBytes = kAttnTileBytes * (1 + 2 * kAttnStages) + 256 + 1024;
+constexpr int kAttnTmemCols = 256;            // S: [0,128)  P: [128,192)  O_j: [192,256)
 
 struct AttnParams {
   __nv_bfloat16* O;
   long long o_sb, o_sh, o_st;
   int H, Tq, Tk;
   float scale_log2;
+  unsigned long long* trace;  // debug: 16 clock64 stamps for CTA (0,0), or nullptr
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+// Registers are allocated per group of 4 warps: the 6 warps of this CTA cost as much as 8, so two resident CTAs
+// need <= 128 registers per thread -- hence the bound of 256 threads although 192 are launched.
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -40,17 +49,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kAttnTileBytes;
   uint8_t* sV = sK + kAttnStages * kAttnTileBytes;
-  uint8_t* sP = sV + kAttnStages * kAttnTileBytes;  // 2 buffers x [2 sub-tiles of 128 x 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAttnTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAttnStages * kAttnTileBytes);
   uint64_t* q_full = bars;
   uint64_t* k_full = q_full + 1;
   uint64_t* v_full = k_full + kAttnStages;
   uint64_t* kv_empty = v_full + kAttnStages;
   uint64_t* s_full = kv_empty + kAttnStages;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 2;
-  uint64_t* o_empty = o_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -58,6 +66,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int b = blockIdx.y / p.H;
   const int h = blockIdx.y - b * p.H;
   const int nkv = (p.Tk + kAttnBlockKV - 1) / kAttnBlockKV;
+#define AT_TRACE(slot)                                                                  \
+  do {                                                                                  \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[slot] = clock64();       \
+  } while (0)
+  if (threadIdx.x == 0) AT_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -69,21 +82,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 128);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<kAttnTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 2 x 64 columns
+  pdl_launch_dependents();  // prologue above touched only shared / tensor memory
+  pdl_wait();
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_P = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 192;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -104,7 +118,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kAttnBlockKV, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);        // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);        // P (TMEM)    x V (MN-major)
       const uint32_t q_addr = smem_u32(sQ);
       auto issue_s = [&](int j) {
         const int st = j % kAttnStages;
@@ -113,31 +127,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t k_addr = smem_u32(sK + st * kAttnTileBytes);
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k)
-          umma_bf16_ss(tmem_S + (j & 1) * kAttnBlockKV, umma_smem_desc_sw128(q_addr + k * 32, 0, 1024),
+          umma_bf16_ss(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 0, 1024),
                        umma_smem_desc_sw128(k_addr + k * 32, 0, 1024), idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) issue_s(j + 1);
-        const int bf = j & 1;
-        const uint32_t u = (j >> 1) & 1;
         const int st = j % kAttnStages;
-        mbar_wait(&p_full[bf], u);
-        mbar_wait(&o_empty[bf], u ^ 1);
-        mbar_wait(&v_full[st], (j / kAttnStages) & 1);
+        mbar_wait(p_full, j & 1);  // softmax(j) has consumed S(j) and published P(j)
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP + bf * 2 * kAttnTileBytes);
+        if (j == 2) AT_TRACE(8);
+        if (j + 1 < nkv) issue_s(j + 1);
+        mbar_wait(&v_full[st], (j / kAttnStages) & 1);
+        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);  // O_{j-1} has been folded into registers
+        tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + st * kAttnTileBytes);
 #pragma unroll
-        for (int kk = 0; kk < kAttnBlockKV / 16; ++kk) {
-          const uint64_t da = umma_smem_desc_sw128(p_addr + (kk >> 2) * kAttnTileBytes + (kk & 3) * 32, 0, 1024);
-          const uint64_t db = umma_smem_desc_sw128(v_addr + kk * 16 * 128, 8192, 1024);
-          umma_bf16_ss(tmem_O + bf * kAttnD, da, db, idesc_o, kk != 0);
-        }
+        for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)
+          umma_bf16_ts(tmem_O, tmem_P + kk * 8, umma_smem_desc_sw128(v_addr + kk * 16 * 128, 8192, 1024), idesc_o,
+                       kk != 0);
         umma_commit(&kv_empty[st]);
-        umma_commit(&o_full[bf]);
+        umma_commit(o_full);
+        if (j == 2) AT_TRACE(9);
       }
     }
   } else {
@@ -145,96 +157,109 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;  // m: running max of the *scaled* scores (log2 domain)
     float acc[kAttnD];
 #pragma unroll
     for (int i = 0; i < kAttnD; ++i) acc[i] = 0.f;
 
     for (int j = 0; j < nkv; ++j) {
-      const int bf = j & 1;
-      const uint32_t u = (j >> 1) & 1;
       const int valid = p.Tk - j * kAttnBlockKV;  // columns >= valid are padding
-      mbar_wait(&s_full[bf], u);
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_S + lane_off + bf * kAttnBlockKV;
-      // pass 1: running maximum of the scaled scores
-      float mx = m;
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(2);
+      // pass 1: row maximum of the raw scores (scale > 0, so scaling commutes with max)
+      // (four independent running maxima: a single fmaxf chain would cost 4 cycles of latency per element)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < kAttnBlockKV; c += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(s_addr + c, v);
+        tmem_ld_32x32b_x32(tmem_S + lane_off + c, v);
         tmem_ld_wait();
+        if (c + 32 > valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(v[i]) * p.scale_log2;
-          mx = fmaxf(mx, (c + i < valid) ? s : -INFINITY);
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= valid) v[i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(v[i + 0]));
+          mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
         }
       }
-      const float alpha = ex2_approx(m - mx);  // m = -inf on the first block -> 0
-      // pass 2: p = 2^(s - max), row sum, bf16 P tile into swizzled smem
-      float rowsum = 0.f;
-      uint8_t* p_row = sP + bf * 2 * kAttnTileBytes + row * 128;
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      const float alpha = ex2_approx(m - m_new);  // m = -inf on the first block -> 0
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(3);
+
+      // fold in the P.V product of the previous block (computed relative to the old max); this also
+      // proves that P(j-1) has been consumed, so the P buffer may be overwritten below
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        if (j == 2 && warp == 2 && lane == 0) AT_TRACE(4);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // two halves: keeps the live register set under the 128 budget
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tmem_O + lane_off + hh * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[hh * 32 + i] = (acc[hh * 32 + i] + __uint_as_float(o[i])) * alpha;
+        }
+        tc_fence_before();
+        mbar_arrive(o_empty);
+      }
+
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(5);
+      // pass 2: p = 2^(s*c - max), row sum, packed bf16 P into TMEM
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // independent partial sums (see pass 1)
 #pragma unroll 1
       for (int c = 0; c < kAttnBlockKV; c += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(s_addr + c, v);
+        tmem_ld_32x32b_x32(tmem_S + lane_off + c, v);
         tmem_ld_wait();
         float e[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = fmaf(__uint_as_float(v[i]), p.scale_log2, -mx);
-          e[i] = (c + i < valid) ? ex2_approx(s) : 0.f;
-          rowsum += e[i];
-        }
-        uint8_t* sub = p_row + (c >> 6) * kAttnTileBytes;  // sub-tile of 64 keys
+        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+        if (c + 32 > valid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = ((c & 63) >> 3) + g;  // 16-byte chunk index within the 128-byte row
-          uint4 o;
-          o.x = pack_bf16x2(e[8 * g + 0], e[8 * g + 1]);
-          o.y = pack_bf16x2(e[8 * g + 2], e[8 * g + 3]);
-          o.z = pack_bf16x2(e[8 * g + 4], e[8 * g + 5]);
-          o.w = pack_bf16x2(e[8 * g + 6], e[8 * g + 7]);
-          *reinterpret_cast<uint4*>(sub + ((chunk ^ (row & 7)) << 4)) = o;
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= valid) e[i] = 0.f;
         }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          rs0 += e[i + 0];
+          rs1 += e[i + 1];
+          rs2 += e[i + 2];
+          rs3 += e[i + 3];
+          pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
+          pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
+        }
+        tmem_st_32x32b_x16(tmem_P + lane_off + (c >> 1), pk);
       }
+      const float rowsum = (rs0 + rs1) + (rs2 + rs3);
       l = fmaf(l, alpha, rowsum);
-      fence_proxy_async_smem();
+      m = m_new;
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(6);
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[bf]);
-
-      // fold in the P.V product of the previous block (it was computed relative to the old max)
-      if (j > 0) {
-        const int pb = (j - 1) & 1;
-        mbar_wait(&o_full[pb], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(tmem_O + lane_off + pb * kAttnD, o0);
-        tmem_ld_32x32b_x32(tmem_O + lane_off + pb * kAttnD + 32, o1);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&o_empty[pb]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          acc[i] = (acc[i] + __uint_as_float(o0[i])) * alpha;
-          acc[32 + i] = (acc[32 + i] + __uint_as_float(o1[i])) * alpha;
-        }
-      }
-      m = mx;
+      mbar_arrive(p_full);
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(7);
     }
     {
-      const int pb = (nkv - 1) & 1;
-      mbar_wait(&o_full[pb], ((nkv - 1) >> 1) & 1);
+      mbar_wait(o_full, (nkv - 1) & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_off + pb * kAttnD, o0);
-      tmem_ld_32x32b_x32(tmem_O + lane_off + pb * kAttnD + 32, o1);
-      tmem_ld_wait();
       const float inv = 1.f / l;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        acc[i] = (acc[i] + __uint_as_float(o0[i])) * inv;
-        acc[32 + i] = (acc[32 + i] + __uint_as_float(o1[i])) * inv;
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_off + hh * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[hh * 32 + i] = (acc[hh * 32 + i] + __uint_as_float(o[i])) * inv;
       }
     }
     if (q0 + row < p.Tq) {
@@ -254,7 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 1) tmem_dealloc<kAttnTmemCols>(tmem_base);
 }
 
 // 4-D map over a bf16 tensor addressed as [b][h][t][d] with element strides (sb, sh, st, 1) and d = 64;
@@ -292,6 +317,7 @@ static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int 
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static unsigned long long* g_attn_trace = nullptr;
 
 }  // namespace st
 
@@ -324,6 +350,9 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
     }
+    // two CTAs per SM need 2 x 82 KB: ask for the largest shared-memory carve-out
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   AttnParams p;
@@ -335,10 +364,30 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   p.Tq = Tq;
   p.Tk = Tk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
   const dim3 grid((Tq + kAttnBlockQ - 1) / kAttnBlockQ, B * H);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  launch_kernel(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
   ST_CHECK_LAUNCH("attn_fwd_kernel");
   return ST_OK;
+}
+
+void st_debug_set_attention_trace(void* buf) { st::g_attn_trace = static_cast<unsigned long long*>(buf); }
+
+// Debug hook: resident CTAs per SM the driver grants the attention kernel (2 expected).
+int st_debug_attention_occupancy(void) {
+  int n = -1;
+  cudaFuncSetAttribute(st::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kAttnSmemBytes);
+  cudaFuncSetAttribute(st::attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, st::attn_fwd_kernel, st::kAttnThreads, st::kAttnSmemBytes);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, st::attn_fwd_kernel);
+  int n48 = -1, n0 = -1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n48, st::attn_fwd_kernel, st::kAttnThreads, 48 * 1024);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, st::attn_fwd_kernel, st::kAttnThreads, 0);
+  printf("attn kernel: regs %d, static smem %zu, max dyn smem %d, local %zu, occupancy @%d B: %d, @48K: %d, @0: %d\n",
+         fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, st::kAttnSmemBytes, n, n48, n0);
+  return n;
 }
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -20,6 +21,14 @@ void set_error(const char* fmt, ...) {
 }
 
 unsigned long long* launch_counter() { return &g_launches; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ST_DISABLE_PDL");
+    return !(e && e[0] && e[0] != '0');
+  }();
+  return on;
+}
 
 int device_sm_count() {
   static int cached[64] = {0};

@@ -24,6 +24,29 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t Ht,
                    uint32_t Wt, uint32_t Nt = 1);
 
+// Programmatic dependent launch (PDL): every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and executes `griddepcontrol.wait` before it touches
+// global memory, so the launch latency and the prologue (barrier init, TMEM allocation, tensor-map
+// prefetch) of kernel N+1 overlap the tail of kernel N -- inside CUDA graphs too (captured as programmatic
+// edges).  ST_DISABLE_PDL=1 falls back to plain stream order.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define ST_CHECK_ARG(cond, ...)        \
   do {                                 \
     if (!(cond)) {                     \

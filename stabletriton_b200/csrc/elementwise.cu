@@ -28,6 +28,8 @@ __device__ __forceinline__ uint4 pack8e(const float (&f)[8]) {
 // ---- GEGLU (reference: kernels/geglu.py:17-26) ---------------------------------------------------
 __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ state, int lds, const __nv_bfloat16* __restrict__ gate,
                              int ldg, __nv_bfloat16* __restrict__ out, int ldo, int rows, int vec_per_row) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(rows) * vec_per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(256)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
                       const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy, int M, int N,
                       int K, int silu_in, int silu_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + warp;
   if (n >= N) return;
@@ -92,6 +96,8 @@ __global__ void __launch_bounds__(256)
 conv3x3_small_c_kernel(const __nv_bfloat16* __restrict__ x, long long xs_n, long long xs_h, long long xs_w,
                        long long xs_c, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
                        __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];  // [9*C][K]
   const int taps = 9 * C;
   for (int i = threadIdx.x; i < taps * K; i += blockDim.x) {
@@ -142,6 +148,8 @@ __global__ void __launch_bounds__(256)
 conv3x3_small_k_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                        const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long ys_n,
                        long long ys_h, long long ys_w, long long ys_c, int N, int H, int W, int C, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t s_raw[];
   __nv_bfloat16* s_w = reinterpret_cast<__nv_bfloat16*>(s_raw);  // [K][9*C]
   const int wlen = K * 9 * C;
@@ -201,6 +209,8 @@ conv3x3_small_k_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
 // ---- im2col 3x3 pad 1 stride s, NHWC -> [N*Ho*Wo, 9*C] (tap-major) --------------------------------
 __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H,
                                  int W, int C, int Ho, int Wo, int stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = C / 8;
   const long long total = static_cast<long long>(N) * Ho * Wo * 9 * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -225,6 +235,8 @@ __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 // ---- nearest 2x upsample, NHWC ---------------------------------------------------------------------
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                   int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = static_cast<long long>(N) * Ho * Wo * cv;
@@ -244,6 +256,8 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 // ---- channel concat ---------------------------------------------------------------------------------
 __global__ void concat_channels_kernel(const __nv_bfloat16* __restrict__ a, int Ca, const __nv_bfloat16* __restrict__ b,
                                        int Cb, __nv_bfloat16* __restrict__ y, long long P) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int va = Ca / 8, vb = Cb / 8, vt = va + vb;
   const long long total = P * vt;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -259,6 +273,8 @@ __global__ void concat_channels_kernel(const __nv_bfloat16* __restrict__ a, int 
 // ---- sinusoidal timestep embedding (unet_pt.py:22-36) -----------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int ldo, int B,
                                           int half) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
   const int b = i / half, j = i - b * half;
@@ -273,6 +289,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bflo
 __global__ void scale_model_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ model_in,
                                          long long n, int copies, const float* __restrict__ sigmas,
                                          const int* __restrict__ step) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float sigma = sigmas[*step];
   const float inv = rsqrtf(sigma * sigma + 1.f);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -286,6 +304,8 @@ __global__ void euler_cfg_update_kernel(const __nv_bfloat16* __restrict__ eps_un
                                         const __nv_bfloat16* __restrict__ eps_cond, float* __restrict__ x,
                                         long long n, float guidance, const float* __restrict__ sigmas,
                                         const int* __restrict__ step) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = *step;
   const float dt = sigmas[s + 1] - sigmas[s];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -297,6 +317,8 @@ __global__ void euler_cfg_update_kernel(const __nv_bfloat16* __restrict__ eps_un
   }
 }
 __global__ void advance_step_kernel(int* step, float* t_out, const float* timesteps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = *step + 1;
   *step = s;
   if (t_out && timesteps) *t_out = timesteps[s];
@@ -323,8 +345,7 @@ int st_geglu_bf16(const void* state, int ld_state, const void* gate, int ld_gate
   ST_CHECK_ARG(ld_state % 8 == 0 && ld_gate % 8 == 0 && ld_out % 8 == 0, "geglu: pitches must be multiples of 8");
   ST_CHECK_ARG(aligned16(state) && aligned16(gate) && aligned16(out), "geglu: pointers must be 16-byte aligned");
   const long long total = static_cast<long long>(rows) * (cols / 8);
-  geglu_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(state), ld_state, static_cast<const __nv_bfloat16*>(gate), ld_gate,
+  launch_kernel(geglu_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(state), ld_state, static_cast<const __nv_bfloat16*>(gate), ld_gate,
       static_cast<__nv_bfloat16*>(out), ld_out, rows, cols / 8);
   ST_CHECK_LAUNCH("geglu_kernel");
   return ST_OK;
@@ -339,8 +360,7 @@ int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const
   ST_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0, "linear_small_m: pitches must be multiples of 8");
   ST_CHECK_ARG(aligned16(x) && aligned16(W), "linear_small_m: pointers must be 16-byte aligned");
   const int warps = 8;
-  linear_small_m_kernel<<<(N + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(W), ldw,
+  launch_kernel(linear_small_m_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(W), ldw,
       static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), ldy, M, N, K, silu_in, silu_out);
   ST_CHECK_LAUNCH("linear_small_m_kernel");
   return ST_OK;
@@ -366,8 +386,7 @@ int st_conv3x3_direct_bf16(const void* x, long long xs_n, long long xs_h, long l
       configured = true;
     }
     const long long total = static_cast<long long>(N) * H * W * (K / 8);
-    conv3x3_small_c_kernel<<<grid_for(total, 256, 4), 256, smem, s>>>(
-        static_cast<const __nv_bfloat16*>(x), xs_n, xs_h, xs_w, xs_c, static_cast<const __nv_bfloat16*>(w),
+    launch_kernel(conv3x3_small_c_kernel, dim3(grid_for(total, 256, 4)), dim3(256), smem, s, static_cast<const __nv_bfloat16*>(x), xs_n, xs_h, xs_w, xs_c, static_cast<const __nv_bfloat16*>(w),
         static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), N, H, W, C, K);
     ST_CHECK_LAUNCH("conv3x3_small_c_kernel");
     return ST_OK;
@@ -388,12 +407,10 @@ int st_conv3x3_direct_bf16(const void* x, long long xs_n, long long xs_h, long l
   const long long pixels = static_cast<long long>(N) * H * W;
   const int grid = grid_for(pixels * 32, 256, 4);
   if (K <= 4)
-    conv3x3_small_k_kernel<4><<<grid, 256, smem, s>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
+    launch_kernel(conv3x3_small_k_kernel<4>, dim3(grid), dim3(256), smem, s, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
         static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), ys_n, ys_h, ys_w, ys_c, N, H, W, C, K);
   else
-    conv3x3_small_k_kernel<8><<<grid, 256, smem, s>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
+    launch_kernel(conv3x3_small_k_kernel<8>, dim3(grid), dim3(256), smem, s, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
         static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), ys_n, ys_h, ys_w, ys_c, N, H, W, C, K);
   ST_CHECK_LAUNCH("conv3x3_small_k_kernel");
   return ST_OK;
@@ -407,8 +424,7 @@ int st_im2col3x3_nhwc_bf16(const void* x, void* col, int N, int H, int W, int C,
   ST_CHECK_ARG(aligned16(x) && aligned16(col), "im2col: pointers must be 16-byte aligned");
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = static_cast<long long>(N) * Ho * Wo * 9 * (C / 8);
-  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(col), N, H, W, C, Ho, Wo, stride);
+  launch_kernel(im2col3x3_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(col), N, H, W, C, Ho, Wo, stride);
   ST_CHECK_LAUNCH("im2col3x3_kernel");
   return ST_OK;
 }
@@ -419,8 +435,7 @@ int st_upsample_nearest2x_nhwc_bf16(const void* x, void* y, int N, int H, int W,
   ST_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample: C (%d) must be a positive multiple of 8", C);
   ST_CHECK_ARG(aligned16(x) && aligned16(y), "upsample: pointers must be 16-byte aligned");
   const long long total = static_cast<long long>(N) * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), N, H, W, C);
+  launch_kernel(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), N, H, W, C);
   ST_CHECK_LAUNCH("upsample2x_kernel");
   return ST_OK;
 }
@@ -431,8 +446,7 @@ int st_concat_channels_bf16(const void* a, int Ca, const void* b, int Cb, void* 
   ST_CHECK_ARG(P > 0 && Ca > 0 && Cb > 0 && Ca % 8 == 0 && Cb % 8 == 0, "concat: channel counts must be multiples of 8");
   ST_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(y), "concat: pointers must be 16-byte aligned");
   const long long total = P * ((Ca + Cb) / 8);
-  concat_channels_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a), Ca, static_cast<const __nv_bfloat16*>(b), Cb,
+  launch_kernel(concat_channels_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a), Ca, static_cast<const __nv_bfloat16*>(b), Cb,
       static_cast<__nv_bfloat16*>(y), P);
   ST_CHECK_LAUNCH("concat_channels_kernel");
   return ST_OK;
@@ -443,8 +457,7 @@ int st_timestep_embedding_bf16(const float* t, void* out, int ldo, int B, int ha
   ST_CHECK_ARG(t && out, "timestep_embedding: null pointer");
   ST_CHECK_ARG(B > 0 && half > 0 && ldo >= 2 * half, "timestep_embedding: bad sizes");
   const int total = B * half;
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      t, static_cast<__nv_bfloat16*>(out), ldo, B, half);
+  launch_kernel(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), t, static_cast<__nv_bfloat16*>(out), ldo, B, half);
   ST_CHECK_LAUNCH("timestep_embedding_kernel");
   return ST_OK;
 }
@@ -454,8 +467,7 @@ int st_scale_model_input(const float* x, void* model_in, long long n, int copies
   using namespace st;
   ST_CHECK_ARG(x && model_in && sigmas && step, "scale_model_input: null pointer");
   ST_CHECK_ARG(n > 0 && copies > 0, "scale_model_input: bad sizes");
-  scale_model_input_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(model_in), n, copies, sigmas, step);
+  launch_kernel(scale_model_input_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, static_cast<__nv_bfloat16*>(model_in), n, copies, sigmas, step);
   ST_CHECK_LAUNCH("scale_model_input_kernel");
   return ST_OK;
 }
@@ -465,8 +477,7 @@ int st_euler_cfg_update(const void* eps_uncond, const void* eps_cond, float* x, 
   using namespace st;
   ST_CHECK_ARG(eps_uncond && x && sigmas && step, "euler_cfg_update: null pointer");
   ST_CHECK_ARG(n > 0, "euler_cfg_update: bad sizes");
-  euler_cfg_update_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(eps_uncond), static_cast<const __nv_bfloat16*>(eps_cond), x, n, guidance,
+  launch_kernel(euler_cfg_update_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(eps_uncond), static_cast<const __nv_bfloat16*>(eps_cond), x, n, guidance,
       sigmas, step);
   ST_CHECK_LAUNCH("euler_cfg_update_kernel");
   return ST_OK;
@@ -475,7 +486,7 @@ int st_euler_cfg_update(const void* eps_uncond, const void* eps_cond, float* x, 
 int st_advance_step(int* step, float* t_out, const float* timesteps, st_stream_t stream) {
   using namespace st;
   ST_CHECK_ARG(step, "advance_step: null pointer");
-  advance_step_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step, t_out, timesteps);
+  launch_kernel(advance_step_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), step, t_out, timesteps);
   ST_CHECK_LAUNCH("advance_step_kernel");
   return ST_OK;
 }

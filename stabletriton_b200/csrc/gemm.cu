@@ -49,7 +49,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kernel<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, td, p);
+  launch_kernel(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, ta, tb, td, p);
   ST_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return ST_OK;
 }

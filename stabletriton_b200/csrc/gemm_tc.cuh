@@ -131,6 +131,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only shared / tensor memory: it may overlap the previous kernel's tail
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) ST_TRACE(1);
 
   if (warp == 0) {

@@ -85,6 +85,8 @@ static GnGeom gn_geometry(int N, int HW, int C, int G) {
 __global__ void __launch_bounds__(kGnMaxThreads)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int cpg,
                 int vecs, int pix_lanes, int pix_per_chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_part[];  // [threads][2][4] : (group, n, mean, m2) for the <=2 groups of a vector
   const int n = blockIdx.y;
   const int chunk = blockIdx.x;
@@ -191,6 +193,8 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma,
                                    const __nv_bfloat16* __restrict__ beta, float* __restrict__ scale_shift, int chunks,
                                    int C, int G, int cpg, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   for (int g = warp; g < G; g += warps) {
@@ -226,6 +230,8 @@ template <bool kSilu>
 __global__ void __launch_bounds__(kGnMaxThreads)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                 const float* __restrict__ scale_shift, int HW, int C, int vecs, int pix_lanes, int pix_per_chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   const int cv = threadIdx.x % vecs;
   const int pl = threadIdx.x / vecs;
@@ -284,6 +290,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
                  const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int M, int N,
                  float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= M) return;
@@ -377,19 +385,19 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
 
   const dim3 grid(g.chunks, N);
   const size_t smem = static_cast<size_t>(g.threads) * 8 * sizeof(float);
-  gn_stats_kernel<<<grid, g.threads, smem, s>>>(static_cast<const __nv_bfloat16*>(x), partial, HW, C, groups, g.cpg,
+  launch_kernel(gn_stats_kernel, dim3(grid), dim3(g.threads), smem, s, static_cast<const __nv_bfloat16*>(x), partial, HW, C, groups, g.cpg,
                                                 g.vecs, g.pix_lanes, g.pix_per_chunk);
   ST_CHECK_LAUNCH("gn_stats_kernel");
-  gn_finalize_kernel<<<N, 256, 0, s>>>(partial, static_cast<const __nv_bfloat16*>(gamma),
+  launch_kernel(gn_finalize_kernel, dim3(N), dim3(256), 0, s, partial, static_cast<const __nv_bfloat16*>(gamma),
                                        static_cast<const __nv_bfloat16*>(beta), scale_shift, g.chunks, C, groups, g.cpg,
                                        eps);
   ST_CHECK_LAUNCH("gn_finalize_kernel");
   if (apply_silu)
-    gn_apply_kernel<true><<<grid, g.threads, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+    launch_kernel(gn_apply_kernel<true>, dim3(grid), dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
                                                      static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs,
                                                      g.pix_lanes, g.pix_per_chunk);
   else
-    gn_apply_kernel<false><<<grid, g.threads, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+    launch_kernel(gn_apply_kernel<false>, dim3(grid), dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
                                                       static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs,
                                                       g.pix_lanes, g.pix_per_chunk);
   ST_CHECK_LAUNCH("gn_apply_kernel");
@@ -415,7 +423,7 @@ int st_layernorm_bf16(const void* x, int ldx, void* y, int ldy, const void* gamm
   const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(beta);
 #define ST_LN_CASE(V)                                                                    \
   case V:                                                                                \
-    layernorm_kernel<V><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gp, bp, M, N, eps);       \
+    launch_kernel(layernorm_kernel<V>, dim3(grid), dim3(256), 0, s, xp, ldx, yp, ldy, gp, bp, M, N, eps);       \
     break;
   switch (vpl <= 3 ? 3 : vpl <= 5 ? 5 : vpl <= 8 ? 8 : 16) {
     ST_LN_CASE(3)

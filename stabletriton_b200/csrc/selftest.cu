@@ -15,6 +15,8 @@
 #include "../../include/stabletriton_b200.h"
 
 extern "C" void st_debug_set_gemm_trace(void* buf);
+extern "C" int st_debug_attention_occupancy(void);
+extern "C" void st_debug_set_attention_trace(void* buf);
 extern "C" int st_conv3x3_direct_bf16(const void*, long long, long long, long long, long long, const void*,
                                       const void*, void*, long long, long long, long long, long long, int, int, int,
                                       int, int, st_stream_t);
@@ -699,6 +701,18 @@ int main(int argc, char** argv) {
     return g_fail ? 1 : 0;
   }
   if (!strcmp(what, "attn1") && argc >= 6) {  // selftest attn1 B H Tq Tk
+    unsigned long long* tr;
+    CK(cudaMalloc(&tr, 16 * 8));
+    CK(cudaMemset(tr, 0, 16 * 8));
+    st_debug_set_attention_trace(tr);
+    test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, false);
+    st_debug_set_attention_trace(nullptr);
+    unsigned long long h[16];
+    CK(cudaMemcpy(h, tr, sizeof h, cudaMemcpyDeviceToHost));
+    const char* nm[10] = {"cta start", "softmax(2): before s_full wait", "s_full ready", "pass 1 (max) done",
+                          "o_full(1) ready", "fold done", "pass 2 (exp, P->TMEM) done", "p_full arrived",
+                          "mma: p_full(2) seen", "mma: S(3)+PV(2) issued"};
+    for (int i = 1; i < 10; ++i) printf("  %-34s %8lld\n", nm[i], (long long)(h[i] - h[0]));
     test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, true);
     return g_fail ? 1 : 0;
   }

@@ -205,6 +205,81 @@ def fuse_qkv_projection(gm: fx.GraphModule) -> int:
     return n
 
 
+def fuse_shared_input_projections(gm: fx.GraphModule) -> int:
+    """Every bias-free projection of one and the same tensor becomes a single GEMM.  In the SDXL UNet this
+    collapses the 70 cross-attention K/V projections of `encoder_hidden_states` (M = 154 rows: far too small
+    to fill the machine one by one) into one (154 x 2048) . (2048 x 166 400) GEMM
+    whose output every attention layer reads through strided column slices."""
+    groups: Dict[Node, List[Node]] = {}
+    for node in gm.graph.nodes:
+        if _is_function(node, W.linear_wrapper_functional) and node.args[2] is None and node.args[3] is False \
+                and isinstance(node.args[1], Node) and node.args[1].op == "get_attr":
+            groups.setdefault(node.args[0], []).append(node)
+    n = 0
+    for src, nodes in groups.items():
+        if len(nodes) < 2:
+            continue
+        weights = [gm.get_buffer(x.args[1].target) for x in nodes]
+        if len({w.shape[1] for w in weights}) != 1:
+            continue
+        name = f"_st_shared_proj_{n}"
+        with torch.no_grad():
+            gm.register_buffer(name, torch.cat(weights, dim=0).contiguous(), persistent=False)
+        first = nodes[0]
+        with gm.graph.inserting_before(first):
+            w = gm.graph.get_attr(name)
+            fused = gm.graph.call_function(W.linear_wrapper_functional, (src, w, None, False))
+        off = 0
+        for node, wt in zip(nodes, weights):
+            with gm.graph.inserting_before(node):
+                piece = gm.graph.call_function(operator.getitem, (fused, (Ellipsis, slice(off, off + wt.shape[0]))))
+            off += wt.shape[0]
+            node.replace_all_uses_with(piece)
+        for x in nodes:  # the per-layer fused weights are no longer referenced
+            gm.graph.erase_node(x)
+        n += 1
+    _finish(gm)
+    for name in [k for k, _ in gm.named_buffers() if k.startswith("_st_fused_proj_")]:
+        if not any(nd.op == "get_attr" and nd.target == name for nd in gm.graph.nodes):
+            delattr(gm, name)
+    return n
+
+
+def fuse_time_embedding_projections(gm: fx.GraphModule) -> int:
+    """Linear(SiLU(emb)) for every resnet (17 in SDXL, unet_pt.py:81-82) reads the same `emb`: one tiny-M GEMM
+    over the row-concatenated weights (13 760 x 1280), each resnet taking its column slice."""
+    groups: Dict[Node, List[Node]] = {}
+    for node in gm.graph.nodes:
+        m = _module_of(gm, node, nn.Linear)
+        if m is None or m.bias is None:
+            continue
+        src = node.args[0]
+        if _is_silu(gm, src) and isinstance(src.args[0], Node):
+            groups.setdefault(src.args[0], []).append(node)
+    n = 0
+    for emb, nodes in groups.items():
+        mods = [gm.get_submodule(x.target) for x in nodes]
+        if len(nodes) < 2 or len({m.in_features for m in mods}) != 1:
+            continue
+        wname, bname = f"_st_temb_proj_w_{n}", f"_st_temb_proj_b_{n}"
+        with torch.no_grad():
+            gm.register_buffer(wname, torch.cat([m.weight.detach() for m in mods], dim=0).contiguous(), persistent=False)
+            gm.register_buffer(bname, torch.cat([m.bias.detach() for m in mods], dim=0).contiguous(), persistent=False)
+        first = min(nodes, key=lambda x: list(gm.graph.nodes).index(x))
+        with gm.graph.inserting_before(first):
+            w, b = gm.graph.get_attr(wname), gm.graph.get_attr(bname)
+            fused = gm.graph.call_function(W.linear_wrapper_functional, (emb, w, b, False), {"silu_input": True})
+        off = 0
+        for node, m in zip(nodes, mods):
+            with gm.graph.inserting_before(node):
+                piece = gm.graph.call_function(operator.getitem, (fused, (Ellipsis, slice(off, off + m.out_features))))
+            off += m.out_features
+            node.replace_all_uses_with(piece)
+        n += 1
+    _finish(gm)
+    return n
+
+
 def _geglu_parts(gm, mul: Node):
     """mul == state * gelu(gate) -> (state, gate) or None."""
     if not (_is_function(mul, *_MUL) and len(mul.args) == 2):

@@ -35,6 +35,8 @@ def replace_backend(gm: fx.GraphModule, report: Dict[str, int] | None = None) ->
         ("remove_dropout", P.remove_dropout),
         ("fuse_attention", P.fuse_attention),
         ("fuse_qkv_projection", P.fuse_qkv_projection),
+        ("fuse_shared_input_projections", P.fuse_shared_input_projections),
+        ("fuse_time_embedding_projections", P.fuse_time_embedding_projections),
         ("fuse_linear_geglu", P.fuse_linear_geglu),
         ("fuse_geglu", P.fuse_geglu),
         ("fuse_proj_out_residual", P.fuse_proj_out_residual),

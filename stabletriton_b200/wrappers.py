@@ -39,8 +39,8 @@ def linear_wrapper(v: torch.Tensor, linear: torch.nn.Linear, activation: bool,
 
 
 def linear_wrapper_functional(v: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
-                              activation: bool) -> torch.Tensor:
-    return K.linear(v, weight, bias, activation=activation)
+                              activation: bool, silu_input: bool = False) -> torch.Tensor:
+    return K.linear(v, weight, bias, activation=activation, silu_input=silu_input)
 
 
 def linear_geglu_wrapper(v: torch.Tensor, linear: torch.nn.Linear) -> torch.Tensor:

@@ -32,6 +32,11 @@ def test_tiny_rewrite_leaves_no_module_calls_and_preserves_output():
     left = P.census(gm)
     assert not [k for k in left if k.startswith("module:")], left
     assert left["attention_wrapper"] == 34 and left["linear_geglu_wrapper"] == 17
+    assert gm.pass_report["fuse_shared_input_projections"] == 1  # all cross-attention K/V projections: one GEMM
+    # 17 cross-attention layers (5 at 128 channels, 12 at 256): K and V rows stacked, context width 128
+    assert gm.get_buffer("_st_shared_proj_0").shape == (2 * (5 * 128 + 12 * 256), 128)
+    assert not [k for k, _ in gm.named_buffers() if k.startswith("_st_fused_proj_")
+                and gm.get_buffer(k).shape[1] == 128 and gm.get_buffer(k).shape[0] in (256, 512)]
     assert left["group_norm_wrapper"] == 46 and left["conv2d_wrapper"] == 51 and left["concat_wrapper"] == 9
     inp = synth.synth_inputs(2, 16, cfg, seed=5)
     with torch.no_grad():
@@ -65,8 +70,9 @@ def test_pass_counts_on_sdxl_architecture():
     assert report["fuse_proj_out_residual"] == 11 and report["replace_cat"] == 9 and report["replace_timesteps"] == 2
     census = P.census(gm)
     assert not [k for k in census if k.startswith("module:")], census
-    # 743 Linears: 70 GEGLU + every other one behind linear_wrapper
-    assert census["linear_geglu_wrapper"] + census["linear_wrapper"] == 743
+    # 743 Linears: 70 GEGLU, the 17 resnet time-embedding projections batched into one GEMM, the rest 1:1
+    assert report["fuse_time_embedding_projections"] == 1 and census["linear_wrapper_functional"] == 1
+    assert census["linear_geglu_wrapper"] + census["linear_wrapper"] == 743 - 17
 
 
 @pytest.mark.skipif(not os.path.exists(REF_FILE), reason="reference not mounted")
