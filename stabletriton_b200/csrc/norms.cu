@@ -1,7 +1,7 @@
 // Bandwidth-bound normalisation kernels: GroupNorm(+SiLU) on NHWC and LayerNorm over the last dim.
-// 128-bit coalesced loads/stores, fp32 statistics (shifted sums per thread, Chan/Welford merges
-// across threads / CTAs), one HBM read + one write of the activation (the second GroupNorm read is
-// served by the 126 MB L2).
+// 128-bit coalesced loads/stores, fp32 statistics (per-CTA shifted sums in registers and shared
+// memory, warp-shuffle reductions, Chan-style merge of the per-CTA (n, mean, M2) triples), one HBM
+// read + one write of the activation (the second GroupNorm read is served by the 126 MB L2).
 //
 // Replaces (reference): kernels/groupnorm.py:24-161 (semantics fixed to torch.nn.GroupNorm on 4-D
 // input) and kernels/layer_norm.py:114-346.
@@ -9,22 +9,6 @@
 #include "ptx.cuh"
 
 namespace st {
-
-struct Welford {
-  float n, mean, m2;
-};
-
-__device__ __forceinline__ Welford welford_merge(Welford a, Welford b) {
-  if (b.n == 0.f) return a;
-  if (a.n == 0.f) return b;
-  Welford r;
-  r.n = a.n + b.n;
-  const float d = b.mean - a.mean;
-  const float f = b.n / r.n;
-  r.mean = a.mean + d * f;
-  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
-  return r;
-}
 
 __device__ __forceinline__ uint4 ld_nc_16(const void* p) {
   uint4 r;
@@ -47,16 +31,25 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 // GroupNorm
 //   workspace layout (floats):  partial[N][chunks][G][3] (n, mean, M2)  |  scale_shift[N][C][2]
+//   kernel 1 (stats): every CTA reduces a pixel range of one image for all channels -- fully coalesced
+//     16-byte loads -- into per-channel shifted sums (shift = the CTA's first pixel, so |mean| >> std
+//     cannot cancel), folds them into per-group (n, mean, M2) and publishes them; the last CTA of an
+//     image to arrive (atomic ticket) merges the chunks and writes per-channel scale/shift.
+//   kernel 2 (apply): y = silu?(x * scale_c + shift_c); the second read of x is served by the L2.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGnMaxThreads = 512;
+constexpr int kGnMaxImages = 4096;
+__device__ unsigned int g_gn_arrivals[kGnMaxImages];  // per-image tickets; the finalising CTA resets its own
 
 struct GnGeom {
   int N, HW, C, G, cpg;
-  int vecs;          // C / 8 : 16-byte vectors per pixel
-  int threads;       // multiple of vecs, <= 512
-  int pix_lanes;     // threads / vecs
-  int chunks;        // CTAs per image
-  int pix_per_chunk; // ceil(HW / chunks)
+  int vecs;             // C / 8 : 16-byte vectors per pixel
+  int threads;          // multiple of vecs, <= 512
+  int pix_lanes;        // threads / vecs
+  int chunks;           // stats CTAs per image
+  int pix_per_chunk;    // ceil(HW / chunks)
+  int a_chunks;         // apply CTAs per image
+  int a_pix_per_chunk;
 };
 
 static GnGeom gn_geometry(int N, int HW, int C, int G) {
@@ -70,46 +63,63 @@ static GnGeom gn_geometry(int N, int HW, int C, int G) {
   g.pix_lanes = kGnMaxThreads / g.vecs;
   if (g.pix_lanes < 1) g.pix_lanes = 1;
   g.threads = g.pix_lanes * g.vecs;
-  // enough CTAs for ~4 per SM, but at least 4 passes of work per CTA
   const int sms = device_sm_count();
-  int chunks = (4 * sms + N - 1) / N;
-  const int max_chunks = (HW + 4 * g.pix_lanes - 1) / (4 * g.pix_lanes);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  g.pix_per_chunk = (HW + chunks - 1) / chunks;
-  g.chunks = (HW + g.pix_per_chunk - 1) / g.pix_per_chunk;
+  auto split = [&](int ctas_total, int min_passes, int* chunks, int* per) {
+    int c = (ctas_total + N - 1) / N;
+    const int max_c = (HW + min_passes * g.pix_lanes - 1) / (min_passes * g.pix_lanes);
+    if (c > max_c) c = max_c;
+    if (c < 1) c = 1;
+    *per = (HW + c - 1) / c;
+    *chunks = (HW + *per - 1) / *per;
+  };
+  split(2 * sms, 4, &g.chunks, &g.pix_per_chunk);      // stats: ~2 CTAs per SM, >= 4 pixels per thread
+  split(4 * sms, 4, &g.a_chunks, &g.a_pix_per_chunk);  // apply: ~4 CTAs per SM
   return g;
 }
 
-// Pass 1: per-CTA partial statistics of every group over a range of pixels.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __global__ void __launch_bounds__(kGnMaxThreads)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int cpg,
-                int vecs, int pix_lanes, int pix_per_chunk) {
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial,
+                const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                float* __restrict__ scale_shift, int HW, int C, int G, int cpg, int vecs, int pix_lanes,
+                int pix_per_chunk, float eps) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float s_part[];  // [threads][2][4] : (group, n, mean, m2) for the <=2 groups of a vector
+  extern __shared__ float s_gn[];  // [C] shift | [C] sum(x - shift) | [C] sum((x - shift)^2) | per-thread partials
+  float* s_shift = s_gn;
+  float* s_sum = s_gn + C;
+  float* s_sq = s_gn + 2 * C;
+  float* s_part = s_gn + 3 * C;    // [pix_lanes][2][C]: fixed-order (deterministic) cross-thread reduction
+  __shared__ int s_last;
   const int n = blockIdx.y;
   const int chunk = blockIdx.x;
+  const int chunks = gridDim.x;
   const int cv = threadIdx.x % vecs;
   const int pl = threadIdx.x / vecs;
   const int pb = chunk * pix_per_chunk;
   const int pe = min(pb + pix_per_chunk, HW);
   const __nv_bfloat16* base = x + (static_cast<size_t>(n) * HW) * C + cv * 8;
 
-  // shifted sums: shift = first value this thread sees, per channel (robust to |mean| >> std)
-  float shift[8], s1[8], s2[8];
-  float cnt = 0.f;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) shift[e] = s1[e] = s2[e] = 0.f;
-  int pix = pb + pl;
-  if (pix < pe) {
+  if (pl == 0) {
     float f[8];
-    unpack8(ld_nc_16(base + static_cast<size_t>(pix) * C), f);
+    unpack8(ld_nc_16(base + static_cast<size_t>(pb) * C), f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) shift[e] = f[e];
-    cnt = 1.f;
-    pix += pix_lanes;
+    for (int e = 0; e < 8; ++e) s_shift[cv * 8 + e] = f[e];
   }
+  __syncthreads();
+  float shift[8], s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    shift[e] = s_shift[cv * 8 + e];
+    s1[e] = 0.f;
+    s2[e] = 0.f;
+  }
+  int pix = pb + pl;
   for (; pix + 3 * pix_lanes < pe; pix += 4 * pix_lanes) {
     uint4 u[4];
 #pragma unroll
@@ -125,7 +135,6 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
         s2[e] = fmaf(d, d, s2[e]);
       }
     }
-    cnt += 4.f;
   }
   for (; pix < pe; pix += pix_lanes) {
     float f[8];
@@ -136,83 +145,75 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
       s1[e] += d;
       s2[e] = fmaf(d, d, s2[e]);
     }
-    cnt += 1.f;
   }
-
-  // per-channel (n, mean, M2) -> merge the 8 channels into the (at most two) groups they belong to
-  const int c0 = cv * 8;
-  const int g_lo = c0 / cpg;
-  const int g_hi = (c0 + 7) / cpg;
-  Welford w_lo{0.f, 0.f, 0.f}, w_hi{0.f, 0.f, 0.f};
-  if (cnt > 0.f) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      Welford w;
-      w.n = cnt;
-      const float m = s1[e] / cnt;
-      w.mean = shift[e] + m;
-      w.m2 = fmaxf(s2[e] - s1[e] * m, 0.f);
-      if ((c0 + e) / cpg == g_lo)
-        w_lo = welford_merge(w_lo, w);
-      else
-        w_hi = welford_merge(w_hi, w);
+  {
+    float* mine = s_part + static_cast<size_t>(pl) * 2 * C + cv * 8;
+    *reinterpret_cast<float4*>(mine) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    *reinterpret_cast<float4*>(mine + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+    *reinterpret_cast<float4*>(mine + C) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    *reinterpret_cast<float4*>(mine + C + 4) = make_float4(s2[4], s2[5], s2[6], s2[7]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < pix_lanes; ++l) {
+      a += s_part[static_cast<size_t>(l) * 2 * C + c];
+      q += s_part[static_cast<size_t>(l) * 2 * C + C + c];
     }
+    s_sum[c] = a;
+    s_sq[c] = q;
   }
-  float* sp = s_part + threadIdx.x * 8;
-  sp[0] = __int_as_float(g_lo);
-  sp[1] = w_lo.n;
-  sp[2] = w_lo.mean;
-  sp[3] = w_lo.m2;
-  sp[4] = __int_as_float(g_hi == g_lo ? -1 : g_hi);
-  sp[5] = w_hi.n;
-  sp[6] = w_hi.mean;
-  sp[7] = w_hi.m2;
   __syncthreads();
 
-  // one thread per group gathers the partials of the vectors overlapping its channels
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    const int v_lo = (g * cpg) / 8;
-    const int v_hi = (g * cpg + cpg - 1) / 8;
-    Welford acc{0.f, 0.f, 0.f};
-    for (int l = 0; l < pix_lanes; ++l) {
-      for (int v = v_lo; v <= v_hi; ++v) {
-        const float* q = s_part + (l * vecs + v) * 8;
-        if (__float_as_int(q[0]) == g) acc = welford_merge(acc, Welford{q[1], q[2], q[3]});
-        if (__float_as_int(q[4]) == g) acc = welford_merge(acc, Welford{q[5], q[6], q[7]});
-      }
-    }
-    float* out = partial + ((static_cast<size_t>(n) * gridDim.x + chunk) * G + g) * 3;
-    out[0] = acc.n;
-    out[1] = acc.mean;
-    out[2] = acc.m2;
-  }
-}
-
-// Pass 2: merge chunk partials per (image, group) and emit per-channel scale/shift:
-//   y = x * scale_c + shift_c,  scale_c = gamma_c * rstd_g,  shift_c = beta_c - mean_g * scale_c
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma,
-                                   const __nv_bfloat16* __restrict__ beta, float* __restrict__ scale_shift, int chunks,
-                                   int C, int G, int cpg, float eps) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int n = blockIdx.x;
+  // per-group (n, mean, M2) of this chunk: one warp per group, lanes over the group's channels
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const float cnt = static_cast<float>(pe - pb);
   for (int g = warp; g < G; g += warps) {
-    Welford acc{0.f, 0.f, 0.f};
-    for (int c = lane; c < chunks; c += 32) {
-      const float* q = partial + ((static_cast<size_t>(n) * chunks + c) * G + g) * 3;
-      acc = welford_merge(acc, Welford{q[0], q[1], q[2]});
+    float tot = 0.f;
+    for (int c = lane; c < cpg; c += 32) tot += s_sum[g * cpg + c] + cnt * s_shift[g * cpg + c];
+    tot = warp_sum(tot);
+    const float mean = tot / (cnt * cpg);
+    float m2 = 0.f;
+    for (int c = lane; c < cpg; c += 32) {
+      const float d = mean - s_shift[g * cpg + c];
+      m2 += s_sq[g * cpg + c] - 2.f * d * s_sum[g * cpg + c] + cnt * d * d;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      Welford other;
-      other.n = __shfl_xor_sync(0xffffffffu, acc.n, o);
-      other.mean = __shfl_xor_sync(0xffffffffu, acc.mean, o);
-      other.m2 = __shfl_xor_sync(0xffffffffu, acc.m2, o);
-      acc = welford_merge(acc, other);
+    m2 = warp_sum(m2);
+    if (lane == 0) {
+      float* out = partial + ((static_cast<size_t>(n) * chunks + chunk) * G + g) * 3;
+      out[0] = cnt * cpg;
+      out[1] = mean;
+      out[2] = fmaxf(m2, 0.f);
     }
-    const float var = acc.m2 / acc.n;  // biased, as torch.nn.GroupNorm
-    const float rstd = rsqrtf(var + eps);
+  }
+
+  // ticket: the last CTA of image n merges all chunks
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&g_gn_arrivals[n], 1u) == static_cast<unsigned>(chunks - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int g = warp; g < G; g += warps) {
+    float nsum = 0.f, wsum = 0.f;
+    for (int k = lane; k < chunks; k += 32) {
+      const float* q = partial + ((static_cast<size_t>(n) * chunks + k) * G + g) * 3;
+      const float nk = __ldcg(q), mk = __ldcg(q + 1);
+      nsum += nk;
+      wsum = fmaf(nk, mk, wsum);
+    }
+    nsum = warp_sum(nsum);
+    wsum = warp_sum(wsum);
+    const float mean = wsum / nsum;
+    float m2 = 0.f;
+    for (int k = lane; k < chunks; k += 32) {
+      const float* q = partial + ((static_cast<size_t>(n) * chunks + k) * G + g) * 3;
+      const float nk = __ldcg(q), mk = __ldcg(q + 1), qk = __ldcg(q + 2);
+      const float d = mk - mean;
+      m2 += qk + nk * d * d;
+    }
+    m2 = warp_sum(m2);
+    const float rstd = rsqrtf(m2 / nsum + eps);  // biased variance, as torch.nn.GroupNorm
     for (int c = lane; c < cpg; c += 32) {
       const int ch = g * cpg + c;
       const float ga = gamma ? __bfloat162float(gamma[ch]) : 1.f;
@@ -220,9 +221,10 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, const __nv
       const float sc = ga * rstd;
       float* o = scale_shift + (static_cast<size_t>(n) * C + ch) * 2;
       o[0] = sc;
-      o[1] = be - acc.mean * sc;
+      o[1] = be - mean * sc;
     }
   }
+  if (threadIdx.x == 0) g_gn_arrivals[n] = 0u;
 }
 
 // Pass 3: y = silu?(x * scale + shift), streaming.
@@ -371,6 +373,7 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
   using namespace st;
   ST_CHECK_ARG(x && y && workspace, "groupnorm: null pointer");
   ST_CHECK_ARG(N > 0 && HW > 0 && C > 0 && groups > 0, "groupnorm: sizes must be positive");
+  ST_CHECK_ARG(N <= kGnMaxImages, "groupnorm: at most %d images per call", kGnMaxImages);
   ST_CHECK_ARG(C % groups == 0, "groupnorm: C (%d) not divisible by groups (%d)", C, groups);
   ST_CHECK_ARG(C % 8 == 0, "groupnorm: C (%d) must be a multiple of 8", C);
   ST_CHECK_ARG(C / 8 <= kGnMaxThreads, "groupnorm: C (%d) too large (max %d)", C, 8 * kGnMaxThreads);
@@ -383,23 +386,24 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
   const size_t partial_elems = (static_cast<size_t>(N) * g.chunks * groups * 3 + 3) / 4 * 4;
   float* scale_shift = partial + partial_elems;
 
-  const dim3 grid(g.chunks, N);
-  const size_t smem = static_cast<size_t>(g.threads) * 8 * sizeof(float);
-  launch_kernel(gn_stats_kernel, dim3(grid), dim3(g.threads), smem, s, static_cast<const __nv_bfloat16*>(x), partial, HW, C, groups, g.cpg,
-                                                g.vecs, g.pix_lanes, g.pix_per_chunk);
+  const size_t smem = (static_cast<size_t>(3) * C + static_cast<size_t>(g.pix_lanes) * 2 * C) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    configured = true;
+  }
+  ST_CHECK_ARG(smem <= 96 * 1024, "groupnorm: C (%d) needs too much shared memory", C);
+  launch_kernel(gn_stats_kernel, dim3(g.chunks, N), dim3(g.threads), smem, s, static_cast<const __nv_bfloat16*>(x),
+                partial, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), scale_shift,
+                HW, C, groups, g.cpg, g.vecs, g.pix_lanes, g.pix_per_chunk, eps);
   ST_CHECK_LAUNCH("gn_stats_kernel");
-  launch_kernel(gn_finalize_kernel, dim3(N), dim3(256), 0, s, partial, static_cast<const __nv_bfloat16*>(gamma),
-                                       static_cast<const __nv_bfloat16*>(beta), scale_shift, g.chunks, C, groups, g.cpg,
-                                       eps);
-  ST_CHECK_LAUNCH("gn_finalize_kernel");
+  const dim3 agrid(g.a_chunks, N);
   if (apply_silu)
-    launch_kernel(gn_apply_kernel<true>, dim3(grid), dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
-                                                     static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs,
-                                                     g.pix_lanes, g.pix_per_chunk);
+    launch_kernel(gn_apply_kernel<true>, agrid, dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
+                  static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs, g.pix_lanes, g.a_pix_per_chunk);
   else
-    launch_kernel(gn_apply_kernel<false>, dim3(grid), dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
-                                                      static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs,
-                                                      g.pix_lanes, g.pix_per_chunk);
+    launch_kernel(gn_apply_kernel<false>, agrid, dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
+                  static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs, g.pix_lanes, g.a_pix_per_chunk);
   ST_CHECK_LAUNCH("gn_apply_kernel");
   return ST_OK;
 }
