@@ -2,10 +2,10 @@
 // P.V product all in TMEM, online softmax in fp32 registers (one thread per query row, so row max /
 // sum need no shuffles).
 //
-//   grid = (ceil(Tq / 128), B * H); 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-//   warps 2..5 softmax / accumulate / store.  Two CTAs are resident per SM (<= 82 KB smem, 256 TMEM
-//   columns, <= 168 registers), so while one CTA's softmax warps sit on the MUFU pipe the other CTA's
-//   MMAs keep the tensor pipe busy.
+//   grid = (ceil(Tq / 128), B * H); 320 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+//   warps 2..9 softmax / accumulate / store (two warps per TMEM lane quadrant, each owning half of every
+//   row).  Two CTAs are resident per SM (<= 84 KB smem, 256 TMEM columns, <= 85 registers), so while one
+//   CTA's softmax warps sit on the MUFU pipe the other CTA's MMAs keep the tensor pipe busy.
 //
 //   S = Q K^T        : tcgen05.mma SS (Q, K 128B-swizzled K-major tiles from TMA), 128 fp32 columns
 //   P = 2^(S*c - m)  : written back to TMEM as packed bf16 (64 columns) with tcgen05.st
@@ -26,9 +26,9 @@ constexpr int kAttnBlockQ = 128;
 constexpr int kAttnBlockKV = 128;
 constexpr int kAttnD = 64;
 constexpr int kAttnStages = 2;
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;  // TMA warp + MMA warp + 8 softmax warps
 constexpr int kAttnTileBytes = 128 * 64 * 2;  // any [128 x 64] bf16 tile
-constexpr int kAttnSmemBytes = kAttnTileBytes * (1 + 2 * kAttnStages) + 256 + 1024;
+constexpr int kAttnSmemBytes = kAttnTileBytes * (1 + 2 * kAttnStages) + 256 + 2048 + 1024;  // + barriers + row exchange
 constexpr int kAttnTmemCols = 256;            // S: [0,128)  P: [128,192)  O_j: [192,256)
 
 struct AttnParams {
@@ -39,9 +39,9 @@ struct AttnParams {
   unsigned long long* trace;  // debug: 16 clock64 stamps for CTA (0,0), or nullptr
 };
 
-// Registers are allocated per group of 4 warps: the 6 warps of this CTA cost as much as 8, so two resident CTAs
-// need <= 128 registers per thread -- hence the bound of 256 threads although 192 are launched.
-__global__ void __launch_bounds__(256, 2)
+// Registers are allocated per group of 4 warps: the 10 warps of this CTA cost as much as 12, so two resident
+// CTAs need <= 85 registers per thread -- hence the bound of 384 threads although 320 are launched.
+__global__ void __launch_bounds__(384, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,6 +59,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* o_full = p_full + 1;
   uint64_t* o_empty = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parities][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,9 +84,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
+    mbar_init(o_empty, 256);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<kAttnTmemCols>(tmem_slot);
@@ -154,27 +155,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     // ===================================== softmax / accumulate ===============================
+    // 8 warps: the two warps that share a TMEM lane quadrant split every row -- warp `half` owns score
+    // columns [64*half, 64*half+64) of the block and output columns [32*half, 32*half+32) -- and exchange
+    // the row maximum through shared memory.  Halving the per-thread serial chain (max pass -> fold ->
+    // exp pass) and doubling the warps per scheduler is what hides the MUFU / TMEM latencies.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    float m = -INFINITY, l = 0.f;  // m: running max of the *scaled* scores (log2 domain)
-    float acc[kAttnD];
+    const uint32_t pair_bar = 1 + quad;  // named barrier of this quadrant's two warps
+    float m = -INFINITY, l = 0.f;        // m: running max of the *scaled* scores (log2 domain); l: my half of the row sum
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < kAttnD; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 
     for (int j = 0; j < nkv; ++j) {
-      const int valid = p.Tk - j * kAttnBlockKV;  // columns >= valid are padding
+      const int valid = p.Tk - j * kAttnBlockKV - half * 64;  // my columns >= valid are padding
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(1);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(2);
       // pass 1: row maximum of the raw scores (scale > 0, so scaling commutes with max)
-      // (four independent running maxima: a single fmaxf chain would cost 4 cycles of latency per element)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kAttnBlockKV; c += 32) {
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + c, v);
+        tmem_ld_32x32b_x32(tmem_S + lane_off + half * 64 + c, v);
         tmem_ld_wait();
         if (c + 32 > valid) {
 #pragma unroll
@@ -189,59 +195,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
         }
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float* xrow = s_xch + (j & 1) * 256 + row;
+      xrow[half * 128] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, xrow[(half ^ 1) * 128]);
       const float m_new = fmaxf(m, mx * p.scale_log2);
       const float alpha = ex2_approx(m - m_new);  // m = -inf on the first block -> 0
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(3);
 
-      // fold in the P.V product of the previous block (computed relative to the old max); this also
-      // proves that P(j-1) has been consumed, so the P buffer may be overwritten below
+      // fold in my half of the P.V product of the previous block (computed relative to the old max); this
+      // also proves that P(j-1) has been consumed, so the P buffer may be overwritten below
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
         if (j == 2 && warp == 2 && lane == 0) AT_TRACE(4);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {  // two halves: keeps the live register set under the 128 budget
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(tmem_O + lane_off + hh * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[hh * 32 + i] = (acc[hh * 32 + i] + __uint_as_float(o[i])) * alpha;
-        }
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_off + half * 32, o);
+        tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(o_empty);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = (acc[i] + __uint_as_float(o[i])) * alpha;
       }
-
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(5);
-      // pass 2: p = 2^(s*c - max), row sum, packed bf16 P into TMEM
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // independent partial sums (see pass 1)
-#pragma unroll 1
-      for (int c = 0; c < kAttnBlockKV; c += 32) {
+
+      // pass 2: p = 2^(s*c - max), partial row sum, packed bf16 P into TMEM
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + c, v);
+        tmem_ld_32x32b_x32(tmem_S + lane_off + half * 64 + c, v);
         tmem_ld_wait();
-        float e[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-        if (c + 32 > valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i >= valid) e[i] = 0.f;
-        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          rs0 += e[i + 0];
-          rs1 += e[i + 1];
-          rs2 += e[i + 2];
-          rs3 += e[i + 3];
-          pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
-          pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
+          float e0 = ex2_approx(fmaf(__uint_as_float(v[i + 0]), p.scale_log2, -m_new));
+          float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
+          float e2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), p.scale_log2, -m_new));
+          float e3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), p.scale_log2, -m_new));
+          if (c + 32 > valid) {
+            e0 = (c + i + 0 < valid) ? e0 : 0.f;
+            e1 = (c + i + 1 < valid) ? e1 : 0.f;
+            e2 = (c + i + 2 < valid) ? e2 : 0.f;
+            e3 = (c + i + 3 < valid) ? e3 : 0.f;
+          }
+          rs0 += e0;
+          rs1 += e1;
+          rs2 += e2;
+          rs3 += e3;
+          pk[(i >> 1) + 0] = pack_bf16x2(e0, e1);
+          pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
         }
-        tmem_st_32x32b_x16(tmem_P + lane_off + (c >> 1), pk);
+        tmem_st_32x32b_x16(tmem_P + lane_off + half * 32 + (c >> 1), pk);
       }
-      const float rowsum = (rs0 + rs1) + (rs2 + rs3);
-      l = fmaf(l, alpha, rowsum);
+      l = fmaf(l, alpha, (rs0 + rs1) + (rs2 + rs3));
       m = m_new;
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(6);
       tmem_st_wait();
@@ -252,20 +260,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     {
       mbar_wait(o_full, (nkv - 1) & 1);
       tc_fence_after();
-      const float inv = 1.f / l;
+      // total row sum = my half + the partner's
+      float* xrow = s_xch + (nkv & 1) * 256 + row;
+      xrow[half * 128] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float inv = 1.f / (l + xrow[(half ^ 1) * 128]);
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_off + half * 32, o);
+      tmem_ld_wait();
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tmem_O + lane_off + hh * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[hh * 32 + i] = (acc[hh * 32 + i] + __uint_as_float(o[i])) * inv;
-      }
+      for (int i = 0; i < 32; ++i) acc[i] = (acc[i] + __uint_as_float(o[i])) * inv;
     }
     if (q0 + row < p.Tq) {
-      __nv_bfloat16* orow = p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st;
+      __nv_bfloat16* orow =
+          p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st + half * 32;
 #pragma unroll
-      for (int i = 0; i < kAttnD; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 o;
         o.x = pack_bf16x2(acc[i + 0], acc[i + 1]);
         o.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
