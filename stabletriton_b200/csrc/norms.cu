@@ -7,6 +7,7 @@
 // input) and kernels/layer_norm.py:114-346.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace st {
 
@@ -30,15 +31,17 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm
-//   workspace layout (floats):  partial[N][chunks][G][3] (n, mean, M2)  |  scale_shift[N][C][2]
+//   workspace layout (floats):  partial[N][G][3][chunks] (n, mean, M2)  |  scale_shift[N][C][2]
 //   kernel 1 (stats): every CTA reduces a pixel range of one image for all channels -- fully coalesced
 //     16-byte loads -- into per-channel shifted sums (shift = the CTA's first pixel, so |mean| >> std
 //     cannot cancel), folds them into per-group (n, mean, M2) and publishes them; the last CTA of an
 //     image to arrive (atomic ticket) merges the chunks and writes per-channel scale/shift.
 //   kernel 2 (apply): y = silu?(x * scale_c + shift_c); the second read of x is served by the L2.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGnMaxThreads = 512;
+constexpr int kGnMaxThreads = 320;   // >= C/8 for C <= 2560; small CTAs so that 3 fit on an SM (<= 68 registers)
 constexpr int kGnMaxImages = 4096;
+constexpr int kGnStatsPixPerThread = 8;  // 8 x 16 B in flight per thread
+constexpr int kGnApplyPixPerThread = 6;
 __device__ unsigned int g_gn_arrivals[kGnMaxImages];  // per-image tickets; the finalising CTA resets its own
 
 struct GnGeom {
@@ -64,16 +67,21 @@ static GnGeom gn_geometry(int N, int HW, int C, int G) {
   if (g.pix_lanes < 1) g.pix_lanes = 1;
   g.threads = g.pix_lanes * g.vecs;
   const int sms = device_sm_count();
-  auto split = [&](int ctas_total, int min_passes, int* chunks, int* per) {
+  // Every thread issues ALL of its loads before it consumes any (one memory round trip per CTA instead
+  // of one per loop iteration), so a CTA covers at most kGn*PixPerThread x pix_lanes pixels; subject to
+  // that bound the pixel range is split into ~2 (stats) / ~4 (apply) CTAs per SM.
+  auto split = [&](int ctas_total, int max_per_thread, int* chunks, int* per) {
     int c = (ctas_total + N - 1) / N;
-    const int max_c = (HW + min_passes * g.pix_lanes - 1) / (min_passes * g.pix_lanes);
+    const int min_c = (HW + max_per_thread * g.pix_lanes - 1) / (max_per_thread * g.pix_lanes);
+    const int max_c = (HW + g.pix_lanes - 1) / g.pix_lanes;  // at least one pixel per thread
     if (c > max_c) c = max_c;
+    if (c < min_c) c = min_c;
     if (c < 1) c = 1;
     *per = (HW + c - 1) / c;
     *chunks = (HW + *per - 1) / *per;
   };
-  split(2 * sms, 4, &g.chunks, &g.pix_per_chunk);      // stats: ~2 CTAs per SM, >= 4 pixels per thread
-  split(4 * sms, 4, &g.a_chunks, &g.a_pix_per_chunk);  // apply: ~4 CTAs per SM
+  split(3 * sms, kGnStatsPixPerThread, &g.chunks, &g.pix_per_chunk);
+  split(3 * sms, kGnApplyPixPerThread, &g.a_chunks, &g.a_pix_per_chunk);
   return g;
 }
 
@@ -83,7 +91,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(kGnMaxThreads)
+__global__ void __launch_bounds__(kGnMaxThreads, 3)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial,
                 const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                 float* __restrict__ scale_shift, int HW, int C, int G, int cpg, int vecs, int pix_lanes,
@@ -105,27 +113,28 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   const int pe = min(pb + pix_per_chunk, HW);
   const __nv_bfloat16* base = x + (static_cast<size_t>(n) * HW) * C + cv * 8;
 
-  if (pl == 0) {
-    float f[8];
-    unpack8(ld_nc_16(base + static_cast<size_t>(pb) * C), f);
+  uint4 u[kGnStatsPixPerThread];
+  const uint4 u_shift = ld_nc_16(base + static_cast<size_t>(pb) * C);  // same address for every pixel lane
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s_shift[cv * 8 + e] = f[e];
+  for (int i = 0; i < kGnStatsPixPerThread; ++i) {
+    const int pp = pb + pl + i * pix_lanes;
+    if (pp < pe) u[i] = ld_nc_16(base + static_cast<size_t>(pp) * C);
   }
-  __syncthreads();
   float shift[8], s1[8], s2[8];
+  unpack8(u_shift, shift);
+  if (pl == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_shift[cv * 8 + e] = shift[e];
+  }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    shift[e] = s_shift[cv * 8 + e];
     s1[e] = 0.f;
     s2[e] = 0.f;
   }
-  int pix = pb + pl;
-  for (; pix + 3 * pix_lanes < pe; pix += 4 * pix_lanes) {
-    uint4 u[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) u[i] = ld_nc_16(base + static_cast<size_t>(pix + i * pix_lanes) * C);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kGnStatsPixPerThread; ++i) {
+    const int pp = pb + pl + i * pix_lanes;
+    if (pp < pe) {
       float f[8];
       unpack8(u[i], f);
 #pragma unroll
@@ -134,16 +143,6 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
         s1[e] += d;
         s2[e] = fmaf(d, d, s2[e]);
       }
-    }
-  }
-  for (; pix < pe; pix += pix_lanes) {
-    float f[8];
-    unpack8(ld_nc_16(base + static_cast<size_t>(pix) * C), f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = f[e] - shift[e];
-      s1[e] += d;
-      s2[e] = fmaf(d, d, s2[e]);
     }
   }
   {
@@ -180,10 +179,11 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
     }
     m2 = warp_sum(m2);
     if (lane == 0) {
-      float* out = partial + ((static_cast<size_t>(n) * chunks + chunk) * G + g) * 3;
+      // layout [n][g][3][chunks]: the finalising warp reads each quantity of a group as one coalesced run
+      float* out = partial + ((static_cast<size_t>(n) * G + g) * 3) * chunks + chunk;
       out[0] = cnt * cpg;
-      out[1] = mean;
-      out[2] = fmaxf(m2, 0.f);
+      out[chunks] = mean;
+      out[2 * chunks] = fmaxf(m2, 0.f);
     }
   }
 
@@ -195,22 +195,41 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   if (!s_last) return;
   __threadfence();
   for (int g = warp; g < G; g += warps) {
-    float nsum = 0.f, wsum = 0.f;
-    for (int k = lane; k < chunks; k += 32) {
-      const float* q = partial + ((static_cast<size_t>(n) * chunks + k) * G + g) * 3;
-      const float nk = __ldcg(q), mk = __ldcg(q + 1);
-      nsum += nk;
-      wsum = fmaf(nk, mk, wsum);
+    const float* q = partial + ((static_cast<size_t>(n) * G + g) * 3) * chunks;
+    // every lane fetches all of its chunk triples before reducing: one L2 round trip per group, not 2*chunks/32
+    constexpr int kPer = 8;  // covers 256 chunks per pass
+    float nsum = 0.f, wsum = 0.f, m2 = 0.f;
+    for (int k0 = 0; k0 < chunks; k0 += 32 * kPer) {  // (a second pass only beyond 256 chunks)
+      float nk[kPer], mk[kPer];
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const int k = k0 + lane + 32 * i;
+        nk[i] = k < chunks ? __ldcg(q + k) : 0.f;
+        mk[i] = k < chunks ? __ldcg(q + chunks + k) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        nsum += nk[i];
+        wsum = fmaf(nk[i], mk[i], wsum);
+      }
     }
     nsum = warp_sum(nsum);
     wsum = warp_sum(wsum);
     const float mean = wsum / nsum;
-    float m2 = 0.f;
-    for (int k = lane; k < chunks; k += 32) {
-      const float* q = partial + ((static_cast<size_t>(n) * chunks + k) * G + g) * 3;
-      const float nk = __ldcg(q), mk = __ldcg(q + 1), qk = __ldcg(q + 2);
-      const float d = mk - mean;
-      m2 += qk + nk * d * d;
+    for (int k0 = 0; k0 < chunks; k0 += 32 * kPer) {
+      float nk[kPer], mk[kPer], qk[kPer];
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const int k = k0 + lane + 32 * i;
+        nk[i] = k < chunks ? __ldcg(q + k) : 0.f;
+        mk[i] = k < chunks ? __ldcg(q + chunks + k) : mean;
+        qk[i] = k < chunks ? __ldcg(q + 2 * chunks + k) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const float d = mk[i] - mean;
+        m2 += qk[i] + nk[i] * d * d;
+      }
     }
     m2 = warp_sum(m2);
     const float rstd = rsqrtf(m2 / nsum + eps);  // biased variance, as torch.nn.GroupNorm
@@ -229,7 +248,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
 
 // Pass 3: y = silu?(x * scale + shift), streaming.
 template <bool kSilu>
-__global__ void __launch_bounds__(kGnMaxThreads)
+__global__ void __launch_bounds__(kGnMaxThreads, 3)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                 const float* __restrict__ scale_shift, int HW, int C, int vecs, int pix_lanes, int pix_per_chunk) {
   pdl_launch_dependents();
@@ -254,32 +273,30 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
   const size_t img = (static_cast<size_t>(n) * HW) * C + cv * 8;
   const __nv_bfloat16* xb = x + img;
   __nv_bfloat16* yb = y + img;
-  for (int pix = pb + pl; pix < pe; pix += 4 * pix_lanes) {
-    uint4 u[4];
+  uint4 u[kGnApplyPixPerThread];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pp = pix + i * pix_lanes;
-      if (pp < pe) u[i] = ld_nc_16(xb + static_cast<size_t>(pp) * C);
-    }
+  for (int i = 0; i < kGnApplyPixPerThread; ++i) {
+    const int pp = pb + pl + i * pix_lanes;
+    if (pp < pe) u[i] = ld_nc_16(xb + static_cast<size_t>(pp) * C);
+  }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pp = pix + i * pix_lanes;
-      if (pp < pe) {
-        float f[8];
-        unpack8(u[i], f);
+  for (int i = 0; i < kGnApplyPixPerThread; ++i) {
+    const int pp = pb + pl + i * pix_lanes;
+    if (pp < pe) {
+      float f[8];
+      unpack8(u[i], f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float v = fmaf(f[e], sc[e], sh[e]);
-          if (kSilu) v = silu_f(v);
-          f[e] = v;
-        }
-        uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]);
-        o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]);
-        o.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pp) * C) = o;
+      for (int e = 0; e < 8; ++e) {
+        float v = fmaf(f[e], sc[e], sh[e]);
+        if (kSilu) v = silu_f(v);
+        f[e] = v;
       }
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]);
+      o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]);
+      o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pp) * C) = o;
     }
   }
 }
@@ -386,6 +403,7 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
   const size_t partial_elems = (static_cast<size_t>(N) * g.chunks * groups * 3 + 3) / 4 * 4;
   float* scale_shift = partial + partial_elems;
 
+  static const int dbg = getenv("ST_GN_DEBUG") ? atoi(getenv("ST_GN_DEBUG")) : 0;  // 1: stats only, 2: apply only
   const size_t smem = (static_cast<size_t>(3) * C + static_cast<size_t>(g.pix_lanes) * 2 * C) * sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -393,11 +411,13 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
     configured = true;
   }
   ST_CHECK_ARG(smem <= 96 * 1024, "groupnorm: C (%d) needs too much shared memory", C);
+  if (dbg != 2)
   launch_kernel(gn_stats_kernel, dim3(g.chunks, N), dim3(g.threads), smem, s, static_cast<const __nv_bfloat16*>(x),
                 partial, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), scale_shift,
                 HW, C, groups, g.cpg, g.vecs, g.pix_lanes, g.pix_per_chunk, eps);
   ST_CHECK_LAUNCH("gn_stats_kernel");
   const dim3 agrid(g.a_chunks, N);
+  if (dbg == 1) return ST_OK;
   if (apply_silu)
     launch_kernel(gn_apply_kernel<true>, agrid, dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
                   static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs, g.pix_lanes, g.a_pix_per_chunk);
