@@ -104,6 +104,15 @@ int st_conv3x3_direct_bf16(const void* x, long long xs_n, long long xs_h, long l
  * col: [N*Ho*Wo, 9*C], tap-major (r, s, c) to match the KRSC weight; then st_gemm_bf16. */
 int st_im2col3x3_nhwc_bf16(const void* x, void* col, int N, int H, int W, int C, int stride, st_stream_t stream);
 
+/* conv_in on the tensor cores: im2col for tiny C (9*C <= 64) into [N*H*W, 64] rows (tap-major, zero padded),
+ * then st_gemm_bf16 against the weight padded to (K, 64).  x through element strides, like st_conv3x3_direct_bf16. */
+int st_im2col3x3_smallc_bf16(const void* x, long long xs_n, long long xs_h, long long xs_w, long long xs_c, void* col,
+                             int N, int H, int W, int C, st_stream_t stream);
+
+/* conv_out on the tensor cores: st_conv3x3_nhwc_bf16 with the 4 output channels padded to 8, then this
+ * [N*HW, ld] -> dense NCHW (first C channels) transposer, so the scheduler sees a standard latent. */
+int st_nhwc_to_nchw_bf16(const void* src, int ld, void* dst, int N, int HW, int C, st_stream_t stream);
+
 /* Nearest-neighbour 2x upsample, NHWC (F.interpolate(scale_factor=2, mode="nearest"), unet_pt.py:265). */
 int st_upsample_nearest2x_nhwc_bf16(const void* x, void* y, int N, int H, int W, int C, st_stream_t stream);
 

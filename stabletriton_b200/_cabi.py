@@ -34,6 +34,8 @@ PROTOTYPES = {
     "st_conv3x3_direct_bf16": (I, [P, LL, LL, LL, LL, P, P, P, LL, LL, LL, LL, I, I, I, I, I, P]),
     "st_im2col3x3_nhwc_bf16": (I, [P, P, I, I, I, I, I, P]),
     "st_upsample_nearest2x_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
+    "st_im2col3x3_smallc_bf16": (I, [P, LL, LL, LL, LL, P, I, I, I, I, P]),
+    "st_nhwc_to_nchw_bf16": (I, [P, I, P, I, I, I, P]),
     "st_attention_bf16": (I, [P, LL, LL, LL, P, LL, LL, LL, P, LL, LL, LL, P, LL, LL, LL, I, I, I, I, F, P]),
     "st_timestep_embedding_bf16": (I, [P, P, I, I, I, P]),
     "st_concat_channels_bf16": (I, [P, I, P, I, P, LL, P]),

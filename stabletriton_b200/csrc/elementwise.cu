@@ -232,6 +232,53 @@ __global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
   }
 }
 
+// ---- im2col for tiny C (conv_in: C = 4): rows of 9*C values (tap-major) zero-padded to 64, so that the
+// convolution becomes one K = 64 tensor-core GEMM.  x is addressed through element strides (NCHW or NHWC).
+__global__ void im2col3x3_smallc_kernel(const __nv_bfloat16* __restrict__ x, long long xs_n, long long xs_h,
+                                        long long xs_w, long long xs_c, __nv_bfloat16* __restrict__ col, int N, int H,
+                                        int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = static_cast<long long>(N) * H * W * 8;  // 8 vectors of 8 elements per output row
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i & 7);
+    const long long pix = i >> 3;
+    const int q = static_cast<int>(pix % W);
+    const int p = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int idx = v * 8 + e;
+      unsigned short bits = 0;
+      if (idx < 9 * C) {
+        const int tap = idx / C, c = idx - tap * C;
+        const int ih = p + tap / 3 - 1, iw = q + tap % 3 - 1;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          bits = __bfloat16_as_ushort(x[n * xs_n + ih * xs_h + iw * xs_w + c * xs_c]);
+      }
+      w[e >> 1] |= static_cast<uint32_t>(bits) << ((e & 1) * 16);
+    }
+    *reinterpret_cast<uint4*>(col + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---- [P, ld] rows (NHWC, first C channels) -> dense NCHW; used for the 4-channel conv_out result ----
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld, __nv_bfloat16* __restrict__ dst,
+                                    int N, int HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = static_cast<long long>(N) * C * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int hw = static_cast<int>(i % HW);
+    const int c = static_cast<int>((i / HW) % C);
+    const int n = static_cast<int>(i / (static_cast<long long>(HW) * C));
+    dst[i] = src[(static_cast<long long>(n) * HW + hw) * ld + c];
+  }
+}
+
 // ---- nearest 2x upsample, NHWC ---------------------------------------------------------------------
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                   int W, int C) {
@@ -426,6 +473,30 @@ int st_im2col3x3_nhwc_bf16(const void* x, void* col, int N, int H, int W, int C,
   const long long total = static_cast<long long>(N) * Ho * Wo * 9 * (C / 8);
   launch_kernel(im2col3x3_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(col), N, H, W, C, Ho, Wo, stride);
   ST_CHECK_LAUNCH("im2col3x3_kernel");
+  return ST_OK;
+}
+
+int st_im2col3x3_smallc_bf16(const void* x, long long xs_n, long long xs_h, long long xs_w, long long xs_c, void* col,
+                             int N, int H, int W, int C, st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(x && col, "im2col_smallc: null pointer");
+  ST_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && 9 * C <= 64, "im2col_smallc: needs 9*C <= 64 (got C=%d)", C);
+  ST_CHECK_ARG(aligned16(col), "im2col_smallc: col must be 16-byte aligned");
+  const long long total = static_cast<long long>(N) * H * W * 8;
+  launch_kernel(im2col3x3_smallc_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                static_cast<const __nv_bfloat16*>(x), xs_n, xs_h, xs_w, xs_c, static_cast<__nv_bfloat16*>(col), N, H, W, C);
+  ST_CHECK_LAUNCH("im2col3x3_smallc_kernel");
+  return ST_OK;
+}
+
+int st_nhwc_to_nchw_bf16(const void* src, int ld, void* dst, int N, int HW, int C, st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(src && dst, "nhwc_to_nchw: null pointer");
+  ST_CHECK_ARG(N > 0 && HW > 0 && C > 0 && ld >= C, "nhwc_to_nchw: bad sizes");
+  const long long total = static_cast<long long>(N) * C * HW;
+  launch_kernel(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                static_cast<const __nv_bfloat16*>(src), ld, static_cast<__nv_bfloat16*>(dst), N, HW, C);
+  ST_CHECK_LAUNCH("nhwc_to_nchw_kernel");
   return ST_OK;
 }
 

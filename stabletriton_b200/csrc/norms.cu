@@ -165,9 +165,10 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   __syncthreads();
 
   // per-group (n, mean, M2) of this chunk: one warp per group, lanes over the group's channels
+  // blockDim.x = pix_lanes * C/8 need not be a multiple of 32: only full warps take part in the shuffles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const float cnt = static_cast<float>(pe - pb);
-  for (int g = warp; g < G; g += warps) {
+  for (int g = warp < warps ? warp : G; g < G; g += warps) {
     float tot = 0.f;
     for (int c = lane; c < cpg; c += 32) tot += s_sum[g * cpg + c] + cnt * s_shift[g * cpg + c];
     tot = warp_sum(tot);
@@ -194,7 +195,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int g = warp; g < G; g += warps) {
+  for (int g = warp < warps ? warp : G; g < G; g += warps) {
     const float* q = partial + ((static_cast<size_t>(n) * G + g) * 3) * chunks;
     // every lane fetches all of its chunk triples before reducing: one L2 round trip per group, not 2*chunks/32
     constexpr int kPer = 8;  // covers 256 chunks per pass

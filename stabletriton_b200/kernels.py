@@ -18,6 +18,7 @@ logical shape (N, C, H, W) and NHWC strides; a token tensor (B, T, C) shares the
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -252,6 +253,26 @@ def pack_conv_weight(weight: torch.Tensor) -> torch.Tensor:
     return weight.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
 
 
+_PADDED: dict = {}  # id(tensor) -> (weakref to the tensor, {tag: (version, padded copy)})
+
+
+def _padded(t: torch.Tensor, tag: str, make):
+    """Zero-padded copy of a (tiny) weight / bias, built once per tensor object + version and reused -- the
+    first call happens during warm-up, so CUDA-graph capture only ever sees the cached tensor.  Keyed by the
+    identity of the live tensor object (a data_ptr key could alias a freed tensor of another model)."""
+    key = id(t)
+    entry = _PADDED.get(key)
+    if entry is None or entry[0]() is not t:
+        entry = (weakref.ref(t, lambda _r, k=key: _PADDED.pop(k, None)), {})
+        _PADDED[key] = entry
+    hit = entry[1].get(tag)
+    if hit is None or hit[0] != t._version:
+        with torch.no_grad():
+            hit = (t._version, make())
+        entry[1][tag] = hit
+    return hit[1]
+
+
 def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
     _require_bf16_cuda("upsample_nearest2x", x)
     x = _nhwc(x)
@@ -315,20 +336,41 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     if (r, s) != (3, 3) or padding != 1:
         raise ValueError(f"conv2d: unsupported kernel {r}x{s} / padding {padding}")
 
-    if c <= 8 or k <= 8:  # conv_in / conv_out: CUDA-core direct kernels, arbitrary in/out strides
+    if c <= 7 or k <= 8:  # conv_in / conv_out: reshaped so that they run on the tensor-core GEMM too
         if stride != 1 or temb is not None or residual is not None:
             raise ValueError("conv2d: small-channel path supports plain stride-1 convolution only")
-        if c <= 8:
-            out = _empty_nhwc(n, k, h, w, x)
+        if c <= 7:
+            # conv_in: im2col to [M, 64] (9*C real columns) x weight padded to (K, 64); NCHW input consumed in place
+            wpad = _padded(weight, "smallc", lambda: torch.nn.functional.pad(
+                wp.permute(0, 2, 3, 1).reshape(k, 9 * c), (0, 64 - 9 * c)).contiguous())
+            col = torch.empty((n * h * w, 64), dtype=BF16, device=x.device)
             xs = x.stride()
-            check(L.st_conv3x3_direct_bf16(x.data_ptr(), xs[0], xs[2], xs[3], xs[1], wp.data_ptr(), _ptr(bias),
-                                           out.data_ptr(), h * w * k, w * k, k, 1, n, h, w, c, k, stream), "conv_in")
+            check(L.st_im2col3x3_smallc_bf16(x.data_ptr(), xs[0], xs[2], xs[3], xs[1], col.data_ptr(), n, h, w, c,
+                                             stream), "im2col_smallc")
+            out = _empty_nhwc(n, k, h, w, x)
+            check(L.st_gemm_bf16(col.data_ptr(), 64, wpad.data_ptr(), 64, out.data_ptr(), k, n * h * w, k, 64,
+                                 _ptr(bias), 0, 0, 0, block_n, stream), "conv_in")
+            return out
+        # conv_out: pad the K <= 8 output channels to 8, implicit GEMM, then gather the real channels
+        if c % 64 != 0 or (h * w) % 128 != 0 and 128 % (h * w) != 0:
+            xn = _nhwc(x)  # shapes the tensor-core conv cannot tile: CUDA-core direct kernel
+            out = torch.empty((n, k, h, w), dtype=BF16, device=x.device) if nchw_output else _empty_nhwc(n, k, h, w, x)
+            os_ = out.stride()
+            check(L.st_conv3x3_direct_bf16(xn.data_ptr(), h * w * c, w * c, c, 1, wp.data_ptr(), _ptr(bias),
+                                           out.data_ptr(), os_[0], os_[2], os_[3], os_[1], n, h, w, c, k, stream),
+                  "conv_out")
             return out
         xn = _nhwc(x)
-        out = torch.empty((n, k, h, w), dtype=BF16, device=x.device) if nchw_output else _empty_nhwc(n, k, h, w, x)
-        os_ = out.stride()
-        check(L.st_conv3x3_direct_bf16(xn.data_ptr(), h * w * c, w * c, c, 1, wp.data_ptr(), _ptr(bias),
-                                       out.data_ptr(), os_[0], os_[2], os_[3], os_[1], n, h, w, c, k, stream), "conv_out")
+        w8 = _padded(weight, "k8", lambda: torch.nn.functional.pad(
+            wp.permute(0, 2, 3, 1).reshape(k, 9 * c), (0, 0, 0, 8 - k)).contiguous())
+        b8 = None if bias is None else _padded(bias, "k8", lambda: torch.nn.functional.pad(bias, (0, 8 - k)).contiguous())
+        y8 = torch.empty((n * h * w, 8), dtype=BF16, device=x.device)
+        check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), w8.data_ptr(), _ptr(b8), y8.data_ptr(), n, h, w, c, 8, 0, 0, 0, 0,
+                                     64, stream), "conv_out")
+        if not nchw_output:
+            return y8.view(n, h, w, 8)[..., :k].permute(0, 3, 1, 2)
+        out = torch.empty((n, k, h, w), dtype=BF16, device=x.device)
+        check(L.st_nhwc_to_nchw_bf16(y8.data_ptr(), 8, out.data_ptr(), n, h * w, k, stream), "nhwc_to_nchw")
         return out
 
     xn = _nhwc(x)
