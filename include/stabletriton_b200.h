@@ -43,6 +43,13 @@ const char* st_last_error_string(void);
 unsigned long long st_launch_count(void);
 void st_reset_launch_count(void);
 
+/* Optional fp32 scratch for stream-K GEMMs (small grids with a long K loop: the tiles x k-blocks space is cut into
+ * one equal range per SM, partial tiles are merged through this buffer).  Caller-owned, one per device, shared by
+ * all GEMM / conv launches on one stream; st_workspace_bytes() is the size to allocate.  Stream-K is
+ * experimental and opt-in (environment ST_ENABLE_STREAMK=1): by default every tile is computed by one CTA. */
+size_t st_workspace_bytes(void);
+int st_set_workspace(void* ptr, size_t bytes);
+
 /* ---- GroupNorm (+SiLU), NHWC ------------------------------------------------------------------
  * Replaces groupnorm_wrapper(input, num_groups, weight, bias, eps, activation)
  * (reference: kernels/groupnorm.py:128-161; wrapper optimizers/replace_groupnorm.py:18-19) with

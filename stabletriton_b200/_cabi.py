@@ -24,6 +24,8 @@ PROTOTYPES = {
     "st_last_error_string": (c_char_p, []),
     "st_launch_count": (c_ulonglong, []),
     "st_reset_launch_count": (None, []),
+    "st_workspace_bytes": (c_size_t, []),
+    "st_set_workspace": (I, [P, c_size_t]),
     "st_groupnorm_workspace_bytes": (c_size_t, [I, I, I, I]),
     "st_groupnorm_nhwc_bf16": (I, [P, P, P, P, P, I, I, I, I, F, I, P]),
     "st_layernorm_bf16": (I, [P, I, P, I, P, P, I, I, F, P]),
@@ -53,7 +55,7 @@ class StableTritonError(RuntimeError):
 
 
 _NOT_KERNELS = {"st_version", "st_last_error_string", "st_launch_count", "st_reset_launch_count",
-                "st_groupnorm_workspace_bytes"}
+                "st_groupnorm_workspace_bytes", "st_workspace_bytes", "st_set_workspace"}
 _recording = None  # list of (symbol, args) while a recording is active
 
 

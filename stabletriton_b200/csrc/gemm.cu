@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
+#include <stdlib.h>
+
 namespace st {
 
 // Pick the B-tile width.  Measured cost model (profiles/r01_gemm_trace.txt): a 128 x BLOCK_N x 64
@@ -33,11 +35,11 @@ static int choose_block_n(int M, int n_cols, bool geglu, int K) {
   return best;
 }
 
-template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu>
+template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
                        cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES>;
-  auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu>;
+  auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu, kStreamK>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -48,7 +50,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     configured = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  const long units = static_cast<long>(tiles) * (p.K / kGemmBlockK);
+  const int sms = device_sm_count();
+  // stream-K: every CTA must own at least one (tile, k-block) unit -- an owner waits for its successors
+  const int grid = p.stream_k ? static_cast<int>(units < sms ? units : sms) : (tiles < sms ? tiles : sms);
   launch_kernel(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, ta, tb, td, p);
   ST_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return ST_OK;
@@ -64,7 +69,9 @@ static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     }
   } else {
     switch (block_n) {
-      case 256: return launch_gemm<256, 4, kConvA, false>(ta, tb, td, p, stream);
+      case 256:
+        if (p.stream_k) return launch_gemm<256, 4, kConvA, false, true>(ta, tb, td, p, stream);
+        return launch_gemm<256, 4, kConvA, false>(ta, tb, td, p, stream);
       case 192: return launch_gemm<192, 5, kConvA, false>(ta, tb, td, p, stream);
       case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, td, p, stream);
       case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, td, p, stream);
@@ -75,6 +82,42 @@ static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 }
 
 static unsigned long long* g_gemm_trace = nullptr;  // debug only, see st_debug_set_gemm_trace
+
+// stream-K state: caller-provided fp32 scratch (st_set_workspace) and self-resetting arrival flags
+constexpr int kMaxDevices = 16;
+static void* g_ws_ptr[kMaxDevices] = {nullptr};
+static size_t g_ws_bytes[kMaxDevices] = {0};
+__device__ unsigned g_sk_flags[256 * 32];  // one flag per 128-byte line
+
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
+// Decide whether a GEMM with `tiles` 128x256 tiles and `nkb` k-blocks should run stream-K: only when the
+// tiles do not fill the machine and the K loop is long enough to pay for the fix-up (cycle model as above).
+static bool want_stream_k(long tiles256, int nkb, long tiles_chosen, float** ws, unsigned** flags) {
+  // Experimental, opt-in (ST_ENABLE_STREAMK=1): measured on B200 (profiles/r01_gemm_trace.txt) the fp32
+  // fix-up through L2 costs more than the shorter K loop saves (2048x1280x5120: 55 us vs 33 us plain), and at
+  // 148 active CTAs the 128x256 tiles become L2-fill bound (~730 instead of 554 cycles per k-block).
+  static const bool disabled = [] {
+    const char* e = getenv("ST_ENABLE_STREAMK");
+    return !(e && e[0] && e[0] != '0');
+  }();
+  const int sms = device_sm_count();
+  const int dev = current_device();
+  if (disabled || !g_ws_ptr[dev] || tiles256 >= sms || tiles_chosen > sms || nkb < 16) return false;
+  if (g_ws_bytes[dev] < static_cast<size_t>(sms) * kGemmBlockM * 256 * sizeof(float)) return false;
+  const double cost_plain = 554.0 * nkb + 6000.0;
+  const double cost_sk = 554.0 * ((tiles256 * nkb + sms - 1) / sms) + 10000.0;
+  if (cost_sk > 0.85 * cost_plain) return false;
+  static unsigned* flag_ptr = nullptr;
+  if (!flag_ptr) cudaGetSymbolAddress(reinterpret_cast<void**>(&flag_ptr), g_sk_flags);
+  *ws = static_cast<float*>(g_ws_ptr[dev]);
+  *flags = flag_ptr;
+  return flag_ptr != nullptr;
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -100,7 +143,18 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   ST_CHECK_ARG(!residual || (aligned16(residual) && ldr % 8 == 0 && ldr >= n_out), "gemm: bad residual pitch/alignment");
   ST_CHECK_ARG(!(geglu && (flags & ST_EPI_SILU)), "gemm: GEGLU and SiLU epilogues are exclusive");
 
-  if (block_n == 0) block_n = choose_block_n(M, n_out, geglu, K);
+  float* sk_ws = nullptr;
+  unsigned* sk_flags = nullptr;
+  bool stream_k = false;
+  if (block_n == 0) {
+    block_n = choose_block_n(M, n_out, geglu, K);
+    const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
+    if (!geglu && want_stream_k(mb * ((n_out + 255) / 256), K / kGemmBlockK, mb * ((n_out + block_n - 1) / block_n),
+                                &sk_ws, &sk_flags)) {
+      stream_k = true;
+      block_n = 256;
+    }
+  }
   const int out_cols = geglu ? block_n / 2 : block_n;
 
   GemmParams p{};
@@ -119,6 +173,9 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.rows_per_batch = 1;
   p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
   p.trace = g_gemm_trace;
+  p.stream_k = stream_k ? 1 : 0;
+  p.ws = sk_ws;
+  p.flags = sk_flags;
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, M, K, lda, kGemmBlockM);
@@ -159,7 +216,18 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   ST_CHECK_ARG(!temb || (aligned16(temb) && ld_temb % 8 == 0), "conv3x3: bad temb pitch/alignment");
 
   const int M = N * H * W;
-  if (block_n == 0) block_n = choose_block_n(M, K, false, 9 * C);
+  float* sk_ws = nullptr;
+  unsigned* sk_flags = nullptr;
+  bool stream_k = false;
+  if (block_n == 0) {
+    block_n = choose_block_n(M, K, false, 9 * C);
+    const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
+    if (want_stream_k(mb * ((K + 255) / 256), 9 * C / kGemmBlockK, mb * ((K + block_n - 1) / block_n), &sk_ws,
+                      &sk_flags)) {
+      stream_k = true;
+      block_n = 256;
+    }
+  }
 
   GemmParams p{};
   p.M = M;
@@ -178,6 +246,9 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.rows_per_batch = H * W;
   p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
   p.trace = g_gemm_trace;
+  p.stream_k = stream_k ? 1 : 0;
+  p.ws = sk_ws;
+  p.flags = sk_flags;
   p.conv_H = H;
   p.conv_W = W;
   p.conv_C = C;
@@ -193,6 +264,17 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   rc = make_tmap_2d(&td, y, M, K, K, kGemmBlockM);
   if (rc != ST_OK) return rc;
   return dispatch_gemm<true>(ta, tb, td, p, block_n, false, static_cast<cudaStream_t>(stream));
+}
+
+int st_set_workspace(void* ptr, size_t bytes) {
+  const int dev = st::current_device();
+  st::g_ws_ptr[dev] = ptr;
+  st::g_ws_bytes[dev] = ptr ? bytes : 0;
+  return ST_OK;
+}
+
+size_t st_workspace_bytes(void) {
+  return static_cast<size_t>(st::device_sm_count()) * st::kGemmBlockM * 256 * sizeof(float);
 }
 
 // Debug hook (not part of the product surface): when set, every GEMM/conv CTA writes 8 clock64 stamps

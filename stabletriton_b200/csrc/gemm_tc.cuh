@@ -47,7 +47,13 @@ struct GemmParams {
   int ld_rowbias;
   int rows_per_batch;
   int act_silu;  // apply SiLU after bias
-  unsigned long long* trace;  // debug: 8 clock64 stamps per CTA (see ST_TRACE), or nullptr
+  unsigned long long* trace;  // debug: 12 clock64 stamps per CTA (see ST_TRACE), or nullptr
+  // stream-K (small grids with a long K loop): the tiles x k-blocks space is cut into gridDim.x equal
+  // contiguous ranges; a CTA that starts in the middle of a tile dumps its fp32 partial into
+  // ws[blockIdx.x] and raises flags[blockIdx.x]; the CTA that owns the head of the tile merges them.
+  int stream_k;
+  float* ws;            // [gridDim.x][128][BLOCK_N] fp32
+  unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
   // 4-D (conv) A addressing
   int conv_H, conv_W, conv_C;  // input == output spatial size (3x3, pad 1, stride 1)
   int conv_Wt, conv_Ht;        // tile rectangle, Wt * Ht == 128
@@ -80,7 +86,7 @@ __device__ __forceinline__ void add_bf16x8(float (&x)[8], const uint4& u) {
 }
 
 // kConvA: A through the 4-D NHWC map.  kGeglu: B tile = [BLOCK_N/2 "state" rows | BLOCK_N/2 "gate" rows].
-template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu>
+template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
@@ -106,6 +112,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_k_blocks = p.K / kGemmBlockK;
+  // Work iterator: plain mode = whole tiles blockIdx.x, +gridDim.x, ...; stream-K = one contiguous range of
+  // (tile, k-block) units.  A segment is (tile, [kb0, kb1)).
+  const long long sk_units = static_cast<long long>(num_tiles) * num_k_blocks;
+  const int sk_u0 = kStreamK ? static_cast<int>(sk_units * blockIdx.x / gridDim.x) : 0;
+  const int sk_u1 = kStreamK ? static_cast<int>(sk_units * (blockIdx.x + 1) / gridDim.x) : 0;
+  auto next_segment = [&](int& cursor, int& tile, int& kb0, int& kb1) -> bool {
+    if (kStreamK) {
+      if (cursor >= sk_u1) return false;
+      tile = cursor / num_k_blocks;
+      kb0 = cursor - tile * num_k_blocks;
+      kb1 = min(num_k_blocks, kb0 + (sk_u1 - cursor));
+      cursor += kb1 - kb0;
+    } else {
+      if (cursor >= num_tiles) return false;
+      tile = cursor;
+      kb0 = 0;
+      kb1 = num_k_blocks;
+      cursor += gridDim.x;
+    }
+    return true;
+  };
+  const int cursor0 = kStreamK ? sk_u0 : static_cast<int>(blockIdx.x);
 #define ST_TRACE(slot)                                                      \
   do {                                                                      \
     if (p.trace) p.trace[blockIdx.x * 12 + (slot)] = clock64();              \
@@ -142,7 +170,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       const int cblocks = kConvA ? p.conv_C / kGemmBlockK : 1;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int cursor = cursor0, tile, kb0, kb1;
+      while (next_segment(cursor, tile, kb0, kb1)) {
         const int m_blk = tile % p.num_m_blocks;
         const int n_blk = tile / p.num_m_blocks;
         const int m0 = m_blk * kGemmBlockM;
@@ -154,7 +183,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           p0 = rem / p.conv_W;
           q0 = rem - p0 * p.conv_W;
         }
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_ab + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
@@ -189,21 +218,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int cursor = cursor0, tile, kb0, kb1;
+      bool first_seg = true;
+      while (next_segment(cursor, tile, kb0, kb1)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (tile == blockIdx.x && kb == 0) ST_TRACE(2);
+          if (first_seg && kb == kb0) ST_TRACE(2);
           const uint32_t a_addr = smem_u32(smem_ab + stage * S::kStageBytes);
           const uint32_t b_addr = a_addr + S::kABytes;
 #pragma unroll
           for (int k = 0; k < kGemmBlockK / 16; ++k) {
             const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb != kb0) || (k != 0));
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == STAGES) {
@@ -212,7 +243,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        if (tile == blockIdx.x) ST_TRACE(3);
+        if (first_seg) ST_TRACE(3);
+        first_seg = false;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -236,13 +268,50 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const bool rowbias_per_tile = p.rowbias != nullptr && p.rows_per_batch >= kGemmBlockM;
     const bool rowbias_per_row = p.rowbias != nullptr && !rowbias_per_tile;
     const int tile_row = quad * 32 + lane;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int cursor = cursor0, tile, kb0, kb1;
+    bool first_seg = true;
+    while (next_segment(cursor, tile, kb0, kb1)) {
       const int m_blk = tile % p.num_m_blocks;
       const int n_blk = tile / p.num_m_blocks;
       const int row = m_blk * kGemmBlockM + tile_row;
       const int n0 = n_blk * kOutCols;
       const bool row_ok = row < p.M;
       float* sb = s_bias + acc * BLOCK_N;
+      const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
+
+      if (kStreamK && kb0 > 0) {
+        // ---- stream-K contributor: this CTA entered the tile in the middle of its K range.  Dump the raw
+        // fp32 partial into its workspace slot and publish it; the tile's owner applies the epilogue.
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        float* wrow = p.ws + (static_cast<size_t>(blockIdx.x) * kGemmBlockM + tile_row) * BLOCK_N;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          const int c = g * 64 + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row0 + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<uint4*>(wrow + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        tc_fence_before();
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (etid == 0) {  // one flag per 128-byte line: spinners of other tiles must not slow this store down
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + blockIdx.x * 32), "r"(1u) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        first_seg = false;
+        continue;
+      }
+      // stream-K owner of a tile whose tail was computed by the following CTAs (their first segment)
+      const bool sk_merge = kStreamK && kb1 < num_k_blocks;
 
       // (1) stage this tile's bias (+ per-image row bias) as fp32: sb[0..kOutCols) state / plain,
       //     sb[kOutCols..2*kOutCols) gate.  Buffer `acc` was last read two tiles ago by these same threads.
@@ -280,8 +349,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // (3) accumulator ready
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(4);
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
+      if (first_seg && warp == 2 && lane == 0) ST_TRACE(4);
+      const uint32_t t_row = t_row0;
+      int sk_last = blockIdx.x;  // contributors are CTAs blockIdx.x + 1 .. sk_last
+      if (sk_merge) {
+        const long long tile_end = static_cast<long long>(tile + 1) * num_k_blocks;
+        while (sk_last + 1 < static_cast<int>(gridDim.x) &&
+               sk_units * (sk_last + 1) / gridDim.x < tile_end)
+          ++sk_last;
+        if (etid == 0) {
+          for (int cc = blockIdx.x + 1; cc <= sk_last; ++cc) {
+            unsigned seen = 0;
+            while (true) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + cc * 32) : "memory");
+              if (seen) break;
+              __nanosleep(64);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) {
         if (n0 + g * 64 >= p.n_out) break;  // this 64-column group lies entirely past the matrix edge
@@ -291,11 +378,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld_32x32b_x32(t_row + c, v);
         if (kGeglu) tmem_ld_32x32b_x32(t_row + kOutCols + c, gt);
         tmem_ld_wait();
-        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(7);
+        if (sk_merge) {
+          for (int cc = blockIdx.x + 1; cc <= sk_last; ++cc) {
+            const float* wrow = p.ws + (static_cast<size_t>(cc) * kGemmBlockM + tile_row) * BLOCK_N + c;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 w4 = __ldcg(reinterpret_cast<const float4*>(wrow + i));
+              v[i + 0] = __float_as_uint(__uint_as_float(v[i + 0]) + w4.x);
+              v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + w4.y);
+              v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + w4.z);
+              v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + w4.w);
+            }
+          }
+        }
+        if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(7);
         // the staging tile is reused per group: wait until the previous TMA store has read it
         if (etid == 0) tma_store_wait_read();
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(8);
+        if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(8);
         // All shared-memory reads of this chunk first (the compiler cannot hoist them over the staging
         // stores below: both live in shared memory), then straight-line register math on 32 columns.
         float x[32];
@@ -356,7 +456,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int chunk = half * 4 + (j >> 3);
           *reinterpret_cast<uint4*>(s_out + tile_row * 128 + ((chunk ^ (tile_row & 7)) << 4)) = o;
         }
-        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(9);
+        if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(9);
         // 64 columns staged: hand them to the TMA store engine (clips rows >= M and columns >= n_out)
         fence_proxy_async_smem();
         asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -364,11 +464,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tma_store_2d(&tmap_d, s_out, n0 + g * 64, m_blk * kGemmBlockM);
           tma_store_commit();
         }
-        if (g == 0 && tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(11);
+        if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(11);
+      }
+      if (sk_merge) {  // every partial has been consumed: re-arm the contributors' flags for the next launch
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (etid == 0)
+          for (int cc = blockIdx.x + 1; cc <= sk_last; ++cc) p.flags[cc * 32] = 0u;
       }
       tc_fence_before();
       __syncwarp();
-      if (tile == blockIdx.x && warp == 2 && lane == 0) ST_TRACE(5);
+      if (first_seg && warp == 2 && lane == 0) ST_TRACE(5);
+      first_seg = false;
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) {
         acc = 0;

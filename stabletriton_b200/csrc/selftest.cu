@@ -251,6 +251,8 @@ static void test_gemm() {
   test_gemm_case(2048, 1280, 1280, 0, true, true, 64, true);
   test_gemm_case(2048, 1280, 1280, 0, true, true, 128, true);
   test_gemm_case(2048, 1280, 1280, 0, true, true, 256, true);
+  test_gemm_case(1000, 1280, 5120, 0, true, true, 0, true);    // stream-K with ragged M
+  test_gemm_case(2048, 640, 4096, ST_EPI_SILU, true, false, 0, true);  // stream-K, 48 tiles
   test_gemm_case(2048, 3840, 1280, 0, false, false, 0, true);
   test_gemm_case(2048, 10240, 1280, ST_EPI_GEGLU, true, false, 0, true);
   test_gemm_case(2048, 10240, 1280, ST_EPI_GEGLU, true, false, 128, true);
@@ -650,6 +652,11 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s, sm_%d%d, %d SMs, lib version %d\n", prop.name, prop.major, prop.minor,
          prop.multiProcessorCount, st_version());
+  {
+    void* ws = nullptr;  // stream-K scratch (leaked on purpose: lives for the whole process)
+    CK(cudaMalloc(&ws, st_workspace_bytes()));
+    ST(st_set_workspace(ws, st_workspace_bytes()));
+  }
   if (!strcmp(what, "trace") && argc >= 7) {  // selftest trace M N K flags block_n : per-CTA phase timeline
     const int M = atoi(argv[2]), N = atoi(argv[3]), K = atoi(argv[4]);
     const unsigned flags = (unsigned)atoi(argv[5]);

@@ -48,6 +48,19 @@ def _require_bf16_cuda(name: str, *tensors: Optional[torch.Tensor]) -> None:
             raise TypeError(f"{name}: tensors must be bfloat16 (got {t.dtype})")
 
 
+_WORKSPACE: dict = {}  # device index -> fp32 scratch registered with the library (stream-K partial tiles)
+
+
+def _ensure_workspace(device: torch.device) -> None:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _WORKSPACE:
+        L = _cabi._load()
+        with torch.cuda.device(idx):
+            buf = torch.empty(L.st_workspace_bytes(), dtype=torch.uint8, device=device)
+            check(L.st_set_workspace(buf.data_ptr(), buf.numel()), "set_workspace")
+        _WORKSPACE[idx] = buf
+
+
 def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
@@ -149,6 +162,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     silu_input applies SiLU to x on load (tiny-M path only: the resnet time-embedding projection).
     """
     _require_bf16_cuda("linear", x, weight, bias, residual)
+    _ensure_workspace(x.device)
     if weight.dim() != 2:
         raise ValueError("linear: weight must be 2-D (N, K)")
     n_rows, k = weight.shape
@@ -306,6 +320,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     nchw_output: write a dense NCHW result (conv_out -> the latent the scheduler consumes).
     """
     _require_bf16_cuda("conv2d", x, weight, bias, temb, residual)
+    _ensure_workspace(x.device)
     if x.dim() != 4:
         raise ValueError("conv2d: expected a 4-D input")
     k, c, r, s = weight.shape
