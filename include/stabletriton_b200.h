@@ -33,6 +33,9 @@ extern "C" {
 #define ST_EPI_SILU 1u  /* y = silu(acc + bias)                   (reference: kernels/linear.py:155-157) */
 #define ST_EPI_GEGLU 2u /* y = (acc_s + b_s) * gelu_erf(acc_g + b_g), B = [state rows ; gate rows]
                            (reference: unet_pt.py:155-158 + kernels/geglu.py:11-26)                       */
+#define ST_W_STATIC 4u  /* hint: the weight operand is not written by the kernel launched just before this one on
+                           the stream, so its first tiles may be fetched before the programmatic (PDL) dependency on
+                           that kernel resolves.  Results are identical with or without it.                       */
 
 typedef void* st_stream_t; /* a cudaStream_t / CUstream */
 

@@ -48,6 +48,7 @@ PROTOTYPES = {
 
 ST_EPI_SILU = 1
 ST_EPI_GEGLU = 2
+ST_W_STATIC = 4
 
 
 class StableTritonError(RuntimeError):

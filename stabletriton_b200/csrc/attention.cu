@@ -20,6 +20,9 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace st {
 
 constexpr int kAttnBlockQ = 128;
@@ -37,6 +40,7 @@ struct AttnParams {
   int H, Tq, Tk;
   float scale_log2;
   unsigned long long* trace;  // debug: 16 clock64 stamps for CTA (0,0), or nullptr
+  int skew;                   // pipelined kernel: start-up delay (cycles) of the second exp warp of each quadrant
 };
 
 // Registers are allocated per group of 4 warps: the 10 warps of this CTA cost as much as 12, so two resident
@@ -117,20 +121,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // whole warp in the loop, one elected lane issues (umma_bf16_ss_elect, ptx.cuh)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kAttnBlockKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);        // P (TMEM)    x V (MN-major)
-      const uint32_t q_addr = smem_u32(sQ);
+      const uint64_t desc_q = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+      const uint64_t desc_k0 = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
+      const uint64_t desc_v0 = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+      constexpr uint32_t kTileStep = kAttnTileBytes >> 4;  // descriptor address units (16 bytes)
       auto issue_s = [&](int j) {
         const int st = j % kAttnStages;
         mbar_wait(&k_full[st], (j / kAttnStages) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * kAttnTileBytes);
+        const uint64_t dk = desc_k0 + static_cast<uint64_t>(st * kTileStep);
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k)
-          umma_bf16_ss(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 0, 1024),
-                       umma_smem_desc_sw128(k_addr + k * 32, 0, 1024), idesc_s, k != 0);
-        umma_commit(s_full);
+          umma_bf16_ss_elect(tmem_S, desc_q + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit_elect(s_full);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -138,19 +145,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int st = j % kAttnStages;
         mbar_wait(p_full, j & 1);  // softmax(j) has consumed S(j) and published P(j)
         tc_fence_after();
-        if (j == 2) AT_TRACE(8);
+        if (j == 2 && lane == 0) AT_TRACE(8);
         if (j + 1 < nkv) issue_s(j + 1);
         mbar_wait(&v_full[st], (j / kAttnStages) & 1);
         if (j > 0) mbar_wait(o_empty, (j - 1) & 1);  // O_{j-1} has been folded into registers
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + st * kAttnTileBytes);
+        const uint64_t dv = desc_v0 + static_cast<uint64_t>(st * kTileStep);
 #pragma unroll
-        for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)
-          umma_bf16_ts(tmem_O, tmem_P + kk * 8, umma_smem_desc_sw128(v_addr + kk * 16 * 128, 8192, 1024), idesc_o,
-                       kk != 0);
-        umma_commit(&kv_empty[st]);
-        umma_commit(o_full);
-        if (j == 2) AT_TRACE(9);
+        for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)  // 16 V rows (2 KB) per instruction
+          umma_bf16_ts_elect(tmem_O, tmem_P + kk * 8, dv + 128 * kk, idesc_o, kk != 0);
+        umma_commit_elect(&kv_empty[st]);
+        umma_commit_elect(o_full);
+        if (j == 2 && lane == 0) AT_TRACE(9);
       }
     }
   } else {
@@ -292,6 +298,334 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 1) tmem_dealloc<kAttnTmemCols>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pipelined variant for Tk > 128 (self-attention): ONE CTA per SM that owns all 512 TMEM columns, so S and P
+// are double-buffered and O accumulates in TMEM across the whole K/V sweep; 448 threads, warp-specialised:
+//
+//   warp 0      TMA producer: Q once, K and V rings (4 stages each)
+//   warp 1      MMA issuer:   S(0); for j: S(j+1) -> wait P(j) -> O += P(j) V(j)     (S(j+1) runs under softmax(j))
+//   warps 2-9   exp warps:    two per TMEM lane quadrant, each owning half of every row: stream S(j) out of TMEM
+//               in 16-column chunks (next chunk in flight while this one is processed), p = 2^(s*c - m),
+//               packed bf16 P(j) -> TMEM, partial row sums.  Nothing but the MUFU-bound stream.
+//   warps 10-13 max warps:    one thread per row, run one block AHEAD of the exp warps: exact row max of S(j)
+//               (FMNMX3), decide the row's reference m, publish it through shared memory.  m only moves when
+//               the row max grows by more than 2^8 (lazy rescale: P <= 256, fp32 sums are safe); moving it
+//               multiplies O (in TMEM) by 2^(m_old - m_new) -- rare after the first blocks -- so there is no
+//               per-block read-modify-write of O at all.
+//
+//   TMEM   S0 [0,128)  S1 [128,256)  P0 [256,320)  P1 [320,384)  O [384,448)
+//
+// Per 128x128 block the tensor pipe needs 512 cycles (4 x 64 + 8 x 32), the MUFU pipe 1024 (16 ex2/clk/SM);
+// the two-CTA kernel above spends ~2.7 k cycles per block and SM because each CTA's MMA -> max -> exp -> MMA
+// chain is serial (single S / P buffers in 256 columns) and both CTAs hit the MUFU phase together.
+constexpr int kA3Stages = 4;
+constexpr int kA3Threads = 448;
+constexpr int kA3SmemBytes = kAttnTileBytes * (1 + 2 * kA3Stages) + 256 + 2048 + 1024;
+constexpr int kA3TmemCols = 512;
+constexpr float kA3Tau = 8.f;  // log2 units
+
+__global__ void __launch_bounds__(kA3Threads, 1)
+attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                          const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAttnTileBytes;
+  uint8_t* sV = sK + kA3Stages * kAttnTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kA3Stages * kAttnTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + kA3Stages;
+  uint64_t* v_full = k_empty + kA3Stages;
+  uint64_t* v_empty = v_full + kA3Stages;
+  uint64_t* s_full = v_empty + kA3Stages;  // [2]
+  uint64_t* m_ready = s_full + 2;          // [2]
+  uint64_t* p_full = m_ready + 2;          // [2]
+  uint64_t* pv_done = p_full + 2;          // [2]
+  uint64_t* s_free = pv_done + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  float* s_m = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 buffers][128 rows] references
+  float* s_l = s_m + 256;                                                         // [2 halves][128 rows] row sums
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kAttnBlockQ;
+  const int b = blockIdx.y / p.H;
+  const int h = blockIdx.y - b * p.H;
+  const int nkv = (p.Tk + kAttnBlockKV - 1) / kAttnBlockKV;
+  if (threadIdx.x == 0) AT_TRACE(0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kA3Stages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&m_ready[i], 128);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 256);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kA3TmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_S = tmem_base;        // + 128 * (j & 1)
+  const uint32_t tmem_P = tmem_base + 256;  // + 64 * (j & 1)
+  const uint32_t tmem_O = tmem_base + 384;
+  const int quad = warp & 3;                // TMEM lane quadrant this warp may touch
+  const int row = quad * 32 + lane;
+  const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kAttnTileBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % kA3Stages;
+        const uint32_t ph = (j / kA3Stages) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], kAttnTileBytes);
+        tma_load_4d(sK + st * kAttnTileBytes, &tmap_k, &k_full[st], 0, j * kAttnBlockKV, h, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], kAttnTileBytes);
+        tma_load_4d(sV + st * kAttnTileBytes, &tmap_v, &v_full[st], 0, j * kAttnBlockKV, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kAttnBlockKV, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);        // P (TMEM)    x V (MN-major)
+      const uint64_t desc_q = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+      const uint64_t desc_k0 = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
+      const uint64_t desc_v0 = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+      constexpr uint32_t kTileStep = kAttnTileBytes >> 4;
+      auto issue_s = [&](int j) {
+        const int st = j % kA3Stages;
+        mbar_wait(&k_full[st], (j / kA3Stages) & 1);
+        tc_fence_after();
+        const uint64_t dk = desc_k0 + static_cast<uint64_t>(st * kTileStep);
+        const uint32_t d = tmem_S + (j & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < kAttnD / 16; ++k) umma_bf16_ss_elect(d, desc_q + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit_elect(&k_empty[st]);
+        umma_commit_elect(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (nkv > 1) issue_s(1);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % kA3Stages;
+        // S(j+2) goes out as soon as the exp warps have pulled the last of S(j) out of TMEM (s_free, ~300 cycles
+        // before they publish P(j)); the max warps read S(j) before that (the exp warps wait for m_ready(j)).  So
+        // the S -> max -> reference chain of block j+2 starts more than a block ahead of its use.
+        if (j + 2 < nkv) {
+          mbar_wait(&s_free[j & 1], (j >> 1) & 1);
+          tc_fence_after();
+          issue_s(j + 2);
+        }
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        if (j == 2 && lane == 0) AT_TRACE(8);
+        mbar_wait(&v_full[st], (j / kA3Stages) & 1);
+        tc_fence_after();
+        const uint64_t dv = desc_v0 + static_cast<uint64_t>(st * kTileStep);
+        const uint32_t a = tmem_P + (j & 1) * 64;
+#pragma unroll
+        for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)
+          umma_bf16_ts_elect(tmem_O, a + kk * 8, dv + 128 * kk, idesc_o, (j > 0) || (kk != 0));
+        umma_commit_elect(&v_empty[st]);
+        umma_commit_elect(&pv_done[j & 1]);
+        if (j == 2 && lane == 0) AT_TRACE(9);
+      }
+    }
+  } else if (warp >= 10) {
+    // ===================================== max warps ========================================
+    float m = -INFINITY;  // reference of my row (scaled scores, log2 domain)
+    for (int j = 0; j < nkv; ++j) {
+      const int buf = j & 1;
+      const int valid = p.Tk - j * kAttnBlockKV;  // columns >= valid are padding
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_s = tmem_S + buf * 128 + lane_off;
+      float mx = -INFINITY;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(t_s, va);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t(&cur)[32] = ((c >> 5) & 1) ? vb : va;
+        uint32_t(&nxt)[32] = ((c >> 5) & 1) ? va : vb;
+        if (c + 32 < 128) tmem_ld_32x32b_x32(t_s + c + 32, nxt);
+        if (c + 32 > valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= valid) cur[i] = 0xff800000u;  // -inf
+        }
+        float g[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a0 = max3f(__uint_as_float(cur[8 * q + 0]), __uint_as_float(cur[8 * q + 1]), __uint_as_float(cur[8 * q + 2]));
+          const float a1 = max3f(__uint_as_float(cur[8 * q + 3]), __uint_as_float(cur[8 * q + 4]), __uint_as_float(cur[8 * q + 5]));
+          g[q] = max3f(a0, a1, fmaxf(__uint_as_float(cur[8 * q + 6]), __uint_as_float(cur[8 * q + 7])));
+        }
+        mx = max3f(mx, max3f(g[0], g[1], g[2]), g[3]);
+        tmem_ld_wait();
+      }
+      const float mj = mx * p.scale_log2;  // scale > 0 commutes with max
+      const bool move = mj > m + kA3Tau;   // always true on the first block (m = -inf)
+      const float m_new = move ? mj : m;
+      if (j > 0 && __any_sync(0xffffffffu, move)) {
+        const float f = ex2_approx(m - m_new);  // exactly 1 for rows that keep their reference
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // every P.V issued so far has landed in O
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tmem_O + lane_off + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st_32x32b_x16(tmem_O + lane_off + c, *reinterpret_cast<const uint32_t(*)[16]>(o));
+          tmem_st_32x32b_x16(tmem_O + lane_off + c + 16, *reinterpret_cast<const uint32_t(*)[16]>(o + 16));
+        }
+        tmem_st_wait();
+      }
+      m = m_new;
+      s_m[buf * 128 + row] = m;
+      tc_fence_before();
+      if (j == 2 && warp == 10 && lane == 0) AT_TRACE(12);
+      if (j == 3 && warp == 10 && lane == 0) AT_TRACE(13);
+      mbar_arrive(&m_ready[buf]);  // release: the exp warps' wait acquires s_m and orders the O rescale before P(j)
+    }
+  } else {
+    // ===================================== exp warps ========================================
+    const int half = (warp - 2) >> 2;
+    const uint32_t pair_bar = 1 + quad;
+    float m_prev = -INFINITY, l = 0.f;  // l: my half of the row sum, relative to m_prev
+    // The two warps of a quadrant share an SM sub-partition (scheduler + MUFU).  Started together they stay in
+    // lock step -- both in the barrier / TMEM-latency part of a block, then both fighting for the MUFU.  Half a
+    // block of skew lets one warp's ex2 stream cover the other's latencies (S and P are double-buffered, so a
+    // warp may run up to a block ahead).
+    if (half == 1 && p.skew > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.skew) {
+      }
+    }
+
+    for (int j = 0; j < nkv; ++j) {
+      const int buf = j & 1;
+      const int valid = p.Tk - j * kAttnBlockKV - half * 64;  // my columns >= valid are padding
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(1);
+      if (j == nkv - 1 && warp == 2 && lane == 0) AT_TRACE(10);
+      // the max warps arrive on m_ready(j) after they have seen s_full(j): S(j) is complete
+      mbar_wait(&m_ready[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_s = tmem_S + buf * 128 + lane_off + half * 64;
+      const uint32_t t_p = tmem_P + buf * 64 + lane_off + half * 32;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(t_s, va);
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(2);
+      const float m = s_m[buf * 128 + row];
+      if (m != m_prev) {
+        l *= ex2_approx(m_prev - m);  // first block: l = 0 and 2^(-inf) = 0
+        m_prev = m;
+      }
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(3);
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t(&cur)[32] = ((c >> 5) & 1) ? vb : va;
+        if (c == 0) {
+          tmem_ld_32x32b_x32(t_s + 32, vb);
+        } else {
+          // all of my S(j) is in registers: the MMA warp may overwrite this S buffer with S(j+2)
+          tc_fence_before();
+          mbar_arrive(&s_free[buf]);
+        }
+        if (c + 32 > valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= valid) cur[i] = 0xff800000u;  // -inf -> fma(-inf, c, -m) = -inf -> 2^(-inf) = 0
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(cur[i + 0]), p.scale_log2, -m));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2, -m));
+          const float e2 = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), p.scale_log2, -m));
+          const float e3 = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), p.scale_log2, -m));
+          rs0 += e0;
+          rs1 += e1;
+          rs2 += e2;
+          rs3 += e3;
+          pk[(i >> 1) + 0] = pack_bf16x2(e0, e1);
+          pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
+        }
+        if (c == 0 && j >= 2) {  // P buffer `buf` was last read by P(j-2) V(j-2), issued a whole block ago
+          mbar_wait(&pv_done[buf], ((j >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_32x32b_x16(t_p + (c >> 1), pk);
+        if (c == 0) tmem_ld_wait();
+      }
+      l += (rs0 + rs1) + (rs2 + rs3);
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(6);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[buf]);
+      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(7);
+    }
+    float acc[32];
+    {
+      mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+      tc_fence_after();
+      // total row sum = my half + the partner's (both relative to the row's final reference)
+      s_l[half * 128 + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float inv = 1.f / (l + s_l[(half ^ 1) * 128 + row]);
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_off + half * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(o[i]) * inv;
+    }
+    if (q0 + row < p.Tq) {
+      __nv_bfloat16* orow =
+          p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st + half * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[i + 0], acc[i + 1]);
+        o.y = pack_bf16x2(acc[i + 2], acc[i + 3]);
+        o.z = pack_bf16x2(acc[i + 4], acc[i + 5]);
+        o.w = pack_bf16x2(acc[i + 6], acc[i + 7]);
+        *reinterpret_cast<uint4*>(orow + i) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<kA3TmemCols>(tmem_base);
+  if (threadIdx.x == 0) AT_TRACE(11);
+}
+
 // 4-D map over a bf16 tensor addressed as [b][h][t][d] with element strides (sb, sh, st, 1) and d = 64;
 // box = [1, 1, 128, 64].  Covers both (B, T, H*64) activations (sh = 64, st = row pitch) and the
 // reference's (B, H, T, D) layout (kernels/attention_fa2.py:113-140).  OOB rows (t >= T) read as zero.
@@ -363,6 +697,11 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
     // two CTAs per SM need 2 x 82 KB: ask for the largest shared-memory carve-out
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return ST_ERR_CUDA;
+    }
     configured = true;
   }
   AttnParams p;
@@ -375,9 +714,27 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   p.Tk = Tk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
+  static const int skew = [] {
+    const char* e = getenv("ST_ATTN_SKEW");
+    return e ? atoi(e) : 600;
+  }();
+  p.skew = skew;
   const dim3 grid((Tq + kAttnBlockQ - 1) / kAttnBlockQ, B * H);
-  launch_kernel(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
-  ST_CHECK_LAUNCH("attn_fwd_kernel");
+  // one K/V block (cross-attention, Tk = 77): the two-CTA-per-SM kernel; longer sweeps: the pipelined one
+  static const int force = [] {
+    const char* e = getenv("ST_ATTN_IMPL");  // debug: "2cta" / "pipelined"
+    return !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : 0));
+  }();
+  const bool pipelined = force ? force == 2 : Tk > kAttnBlockKV;
+  if (pipelined) {
+    launch_kernel(attn_fwd_pipelined_kernel, dim3(grid), dim3(kA3Threads), kA3SmemBytes,
+                  static_cast<cudaStream_t>(stream), tq, tk, tv, p);
+    ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
+  } else {
+    launch_kernel(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq,
+                  tk, tv, p);
+    ST_CHECK_LAUNCH("attn_fwd_kernel");
+  }
   return ST_OK;
 }
 

@@ -6,10 +6,11 @@
 
 namespace st {
 
-// Pick the B-tile width.  Measured cost model (profiles/r01_gemm_trace.txt): a 128 x BLOCK_N x 64
-// k-block costs ~512 cycles of tensor pipe whatever BLOCK_N <= 256 is (SS-mode A-read bound), the
-// epilogue costs a few cycles per output column, and tiles are spread over the SMs in waves.  So the
-// widest tile that does not add a wave wins; ties go to the narrower tile (less operand traffic).
+// Tile-width choice from the measured cost model (profiles/r01_gemm_trace.txt, tools/mmabench.cu): per 64-wide
+// k-block a CTA needs max(tensor pipe, operand fill) cycles, where the tensor pipe takes 4 x BLOCK_N/2 cycles
+// (128 x N x 16 runs at its N/2 floor with the warp-convergent issue loop) and the fill moves (128 + BLOCK_N) x
+// 128 bytes at min(88 B/clk per SM, 9.6 KB/clk over all CTAs) out of L2; the epilogue costs a few cycles per
+// output column, and tiles are spread over the SMs in waves.  Ties go to the narrower tile.
 static int choose_block_n(int M, int n_cols, bool geglu, int K) {
   const int sms = device_sm_count();
   const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
@@ -25,7 +26,11 @@ static int choose_block_n(int M, int n_cols, bool geglu, int K) {
     const int nb = (n_cols + out_cols - 1) / out_cols;
     const long tiles = (long)mb * nb;
     const long waves = (tiles + sms - 1) / sms;
-    const double tile_cost = 512.0 * (K / 64) + 1500.0 + 10.0 * out_cols;
+    const double ctas = tiles < sms ? (double)tiles : (double)sms;
+    const double fill_rate = 9600.0 / ctas < 88.0 ? 9600.0 / ctas : 88.0;  // bytes per clock per SM
+    const double fill = (128.0 + bn) * 128.0 / fill_rate;
+    const double mma = 2.0 * bn;
+    const double tile_cost = (fill > mma ? fill : mma) * (K / 64) + 1500.0 + 10.0 * out_cols;
     const double cost = waves * tile_cost;
     if (cost < best_cost * 0.97) {
       best_cost = cost;
@@ -33,6 +38,14 @@ static int choose_block_n(int M, int n_cols, bool geglu, int K) {
     }
   }
   return best;
+}
+
+static int gemm_ramp() {
+  static const int v = [] {
+    const char* e = getenv("ST_GEMM_RAMP");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
 }
 
 template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false>
@@ -174,6 +187,8 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
   p.trace = g_gemm_trace;
   p.stream_k = stream_k ? 1 : 0;
+  p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
+  p.ramp = gemm_ramp();
   p.ws = sk_ws;
   p.flags = sk_flags;
 
@@ -247,6 +262,8 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.act_silu = (flags & ST_EPI_SILU) ? 1 : 0;
   p.trace = g_gemm_trace;
   p.stream_k = stream_k ? 1 : 0;
+  p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
+  p.ramp = gemm_ramp();
   p.ws = sk_ws;
   p.flags = sk_flags;
   p.conv_H = H;

@@ -52,6 +52,8 @@ struct GemmParams {
   // contiguous ranges; a CTA that starts in the middle of a tile dumps its fp32 partial into
   // ws[blockIdx.x] and raises flags[blockIdx.x]; the CTA that owns the head of the tile merges them.
   int stream_k;
+  int ramp;      // debug/tuning: number of k-blocks requested before waiting for the first to land (0 = off)
+  int w_static;  // W is not written by the preceding kernel: prefetch it ahead of the PDL wait
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
   // 4-D (conv) A addressing
@@ -161,14 +163,39 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only shared / tensor memory: it may overlap the previous kernel's tail
   pdl_launch_dependents();
-  pdl_wait();
-  if (threadIdx.x == 0) ST_TRACE(1);
+  if (warp != 0) pdl_wait();
+  if (threadIdx.x == 32) ST_TRACE(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      // The weight operand is not produced by the preceding kernel (p.w_static): start its first tiles
+      // towards shared memory BEFORE the programmatic dependency resolves, so the HBM latency of the
+      // weights (never L2-resident: 5 GB stream per step) hides under the previous kernel's tail.
+      int prefetched = 0;
+      if (p.w_static) {
+        int cursor = cursor0, tile, kb0, kb1;
+        if (next_segment(cursor, tile, kb0, kb1)) {
+          const int n_blk = tile / p.num_m_blocks;
+          prefetched = min(p.ramp > 0 ? min(p.ramp, STAGES) : STAGES, kb1 - kb0);
+          for (int i = 0; i < prefetched; ++i) {
+            uint8_t* sb = smem_ab + i * S::kStageBytes + S::kABytes;
+            const int kb = kb0 + i;
+            mbar_expect_tx(&full_bar[i], S::kStageBytes);
+            if (kGeglu) {
+              const int h0 = n_blk * (BLOCK_N / 2);
+              tma_load_2d(sb, &tmap_b, &full_bar[i], kb * kGemmBlockK, h0);
+              tma_load_2d(sb + S::kBBytes / 2, &tmap_b, &full_bar[i], kb * kGemmBlockK, p.n_out + h0);
+            } else {
+              tma_load_2d(sb, &tmap_b, &full_bar[i], kb * kGemmBlockK, n_blk * BLOCK_N);
+            }
+          }
+        }
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
+      int ramp_left = p.ramp;
       const int cblocks = kConvA ? p.conv_C / kGemmBlockK : 1;
       int cursor = cursor0, tile, kb0, kb1;
       while (next_segment(cursor, tile, kb0, kb1)) {
@@ -184,10 +211,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           q0 = rem - p0 * p.conv_W;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_ab + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          const bool b_in_flight = prefetched > 0;  // first ring pass of the first segment
+          if (b_in_flight) {
+            --prefetched;
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          }
           if (kConvA) {
             const int tap = kb / cblocks;
             const int cb = kb - tap * cblocks;
@@ -196,7 +228,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0);
           }
-          if (kGeglu) {
+          if (b_in_flight) {
+            // weights already on their way
+          } else if (kGeglu) {
             const int h0 = n_blk * (BLOCK_N / 2);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, h0);
             tma_load_2d(sb + S::kBBytes / 2, &tmap_b, &full_bar[stage], kb * kGemmBlockK, p.n_out + h0);
@@ -207,13 +241,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             stage = 0;
             phase ^= 1;
           }
+          // Start-up ramp: requesting the whole ring at once makes stage 0 share the L2->SM fill with
+          // stages 1..STAGES-1 of every CTA, so the first MMA starts only when most of the ring has landed.
+          // Let the first p.ramp stages land before asking for the rest.
+          if (ramp_left > 0 && --ramp_left == 0) mbar_wait(&full_bar[0], 0);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // The whole warp runs this loop (see umma_bf16_ss_elect in ptx.cuh): one elected lane issues, operand
+    // descriptors advance by 64-bit adds from a per-kernel base.
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kGemmBlockM, BLOCK_N, 0, 0);
+      const uint64_t desc_a0 = umma_smem_desc_sw128(smem_u32(smem_ab), 0, 1024);
+      const uint64_t desc_b0 = umma_smem_desc_sw128(smem_u32(smem_ab) + S::kABytes, 0, 1024);
+      constexpr uint32_t kStageStep = S::kStageBytes >> 4;  // descriptor address field counts 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -227,23 +270,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (first_seg && kb == kb0) ST_TRACE(2);
-          const uint32_t a_addr = smem_u32(smem_ab + stage * S::kStageBytes);
-          const uint32_t b_addr = a_addr + S::kABytes;
+          if (first_seg && kb == kb0 && lane == 0) ST_TRACE(2);
+          const uint64_t da = desc_a0 + static_cast<uint64_t>(stage * kStageStep);
+          const uint64_t db = desc_b0 + static_cast<uint64_t>(stage * kStageStep);
 #pragma unroll
-          for (int k = 0; k < kGemmBlockK / 16; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb != kb0) || (k != 0));
-          }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          for (int k = 0; k < kGemmBlockK / 16; ++k)  // +32 bytes of K per instruction = +2 address units
+            umma_bf16_ss_elect(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+          umma_commit_elect(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        if (first_seg) ST_TRACE(3);
+        umma_commit_elect(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (first_seg && lane == 0) ST_TRACE(3);
         first_seg = false;
         if (++acc == 2) {
           acc = 0;

@@ -247,7 +247,14 @@ static void test_gemm() {
   test_gemm_case(130, 72, 64, ST_EPI_SILU, true, true, 64, false);
   test_gemm_case(256, 1280, 320, ST_EPI_GEGLU, true, false, 256, false);
   // SDXL shapes, timed
+  test_gemm_case(128, 128, 64, ST_W_STATIC, false, false, 128, false);      // K shorter than the prefetch depth
+  test_gemm_case(300, 328, 192, ST_W_STATIC, true, true, 192, false);
+  test_gemm_case(256, 1280, 320, ST_EPI_GEGLU | ST_W_STATIC, true, false, 256, false);
   test_gemm_case(2048, 1280, 1280, 0, true, true, 0, true);
+  test_gemm_case(2048, 1280, 1280, ST_W_STATIC, true, true, 0, true);
+  test_gemm_case(2048, 3840, 1280, ST_W_STATIC, false, false, 0, true);
+  test_gemm_case(2048, 10240, 1280, ST_EPI_GEGLU | ST_W_STATIC, true, false, 0, true);
+  test_gemm_case(2048, 1280, 5120, ST_W_STATIC, true, true, 0, true);
   test_gemm_case(2048, 1280, 1280, 0, true, true, 64, true);
   test_gemm_case(2048, 1280, 1280, 0, true, true, 128, true);
   test_gemm_case(2048, 1280, 1280, 0, true, true, 256, true);
@@ -275,12 +282,12 @@ static void test_conv_case(int N, int H, int W, int C, int K, bool temb, bool re
   CK(cudaMalloc(&y, out * 2));
   CK(cudaMemset(y, 0xff, out * 2));
   CK(cudaMalloc(&yref, out * 4));
-  ST(st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, 0, block_n, 0));
+  ST(st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, ST_W_STATIC, block_n, 0));
   CK(cudaDeviceSynchronize());
   ref_conv3x3<<<dim3((K + 127) / 128, N * H * W), 128>>>(x, w, b, yref, N, H, W, C, K, t, r);
   CK(cudaDeviceSynchronize());
   float ms = -1;
-  if (timeit) ms = time_ms([&](cudaStream_t s) { st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, 0, block_n, s); });
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, ST_W_STATIC, block_n, s); });
   char name[128];
   snprintf(name, sizeof name, "conv3x3 N=%d H=%d W=%d C=%d K=%d temb=%d res=%d bn=%d", N, H, W, C, K, temb, res,
            block_n);
@@ -309,7 +316,15 @@ static void test_conv() {
   test_conv_case(2, 32, 32, 2560, 1280, true, false, 0, true);
 }
 
-static void test_attn_case(int B, int H, int Tq, int Tk, bool fused_qkv, bool timeit) {
+// k[b][t][:] *= 1 + growth * t / Tk: later K/V blocks carry much larger scores, which forces the running
+// softmax reference to move many times (the lazy-rescale path of the pipelined kernel)
+__global__ void grow_rows(__nv_bfloat16* k, int T, int C, float growth) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int t = (int)((i / C) % T);
+  k[i] = __float2bfloat16(__bfloat162float(k[i]) * (1.f + growth * t / T));
+}
+
+static void test_attn_case(int B, int H, int Tq, int Tk, bool fused_qkv, bool timeit, float growth = 0.f) {
   const int C = H * 64;
   const int ld = fused_qkv ? 3 * C : C;
   __nv_bfloat16 *q, *k, *v;
@@ -323,6 +338,7 @@ static void test_attn_case(int B, int H, int Tq, int Tk, bool fused_qkv, bool ti
     q = dev_bf16((size_t)B * Tq * C, 1.5f);
     k = dev_bf16((size_t)B * Tk * C, 1.5f);
     v = dev_bf16((size_t)B * Tk * C, 1.0f);
+    if (growth != 0.f) grow_rows<<<(unsigned)((size_t)B * Tk * C / 64), 64>>>(k, Tk, C, growth);
   }
   __nv_bfloat16* o;
   float* oref;
@@ -341,7 +357,7 @@ static void test_attn_case(int B, int H, int Tq, int Tk, bool fused_qkv, bool ti
                         (long long)Tq * C, 64, C, B, H, Tq, Tk, scale, s);
     });
   char name[128];
-  snprintf(name, sizeof name, "attention B=%d H=%d Tq=%d Tk=%d fusedqkv=%d", B, H, Tq, Tk, fused_qkv);
+  snprintf(name, sizeof name, "attention B=%d H=%d Tq=%d Tk=%d fusedqkv=%d growth=%g", B, H, Tq, Tk, fused_qkv, growth);
   report(name, to_host(o, out), to_host_f(oref, out), 2e-2f, ms, 4.0 * B * H * (double)Tq * Tk * 64 * 1e-12,
          "TFLOP/s");
   if (fused_qkv)
@@ -362,6 +378,9 @@ static void test_attn() {
   test_attn_case(2, 3, 200, 77, false, false);
   test_attn_case(1, 2, 384, 333, false, false);
   test_attn_case(2, 2, 256, 256, true, false);
+  test_attn_case(1, 2, 256, 1024, false, false, 24.f);   // reference max moves in (almost) every block
+  test_attn_case(1, 2, 256, 1000, false, false, -0.9f);  // scores shrink: the reference never moves; ragged tail
+  test_attn_case(2, 3, 130, 129, false, false, 6.f);     // second block holds a single key
   test_attn_case(2, 20, 1024, 1024, true, true);
   test_attn_case(2, 10, 4096, 4096, true, true);
   test_attn_case(2, 10, 4096, 77, false, true);
@@ -716,10 +735,13 @@ int main(int argc, char** argv) {
     st_debug_set_attention_trace(nullptr);
     unsigned long long h[16];
     CK(cudaMemcpy(h, tr, sizeof h, cudaMemcpyDeviceToHost));
-    const char* nm[10] = {"cta start", "softmax(2): before s_full wait", "s_full ready", "pass 1 (max) done",
-                          "o_full(1) ready", "fold done", "pass 2 (exp, P->TMEM) done", "p_full arrived",
-                          "mma: p_full(2) seen", "mma: S(3)+PV(2) issued"};
-    for (int i = 1; i < 10; ++i) printf("  %-34s %8lld\n", nm[i], (long long)(h[i] - h[0]));
+    // slot meanings for the pipelined kernel (Tk > 128); the two-CTA kernel fills 1..9 with its own phases
+    const char* nm[14] = {"cta start", "exp warp, block 2: before m_ready wait", "m_ready seen, first S chunk requested",
+                          "reference read", "-", "-", "exp stream done (64 columns)", "p_full arrived",
+                          "mma: p_full(2) seen", "mma: P(2).V(2) issued", "exp warp, last block: before wait",
+                          "cta exit", "max warp: m(2) published", "max warp: m(3) published"};
+    for (int i = 1; i < 14; ++i)
+      if (h[i]) printf("  %-42s %8lld\n", nm[i], (long long)(h[i] - h[0]));
     test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, true);
     return g_fail ? 1 : 0;
   }

@@ -24,7 +24,7 @@ from typing import Optional
 import torch
 
 from . import _cabi
-from ._cabi import ST_EPI_GEGLU, ST_EPI_SILU, check, lib
+from ._cabi import ST_EPI_GEGLU, ST_EPI_SILU, ST_W_STATIC, check, lib
 
 BF16 = torch.bfloat16
 
@@ -188,7 +188,9 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         rr, _, ldr = _rows(residual)
         res_ptr = rr.data_ptr()
         residual = rr  # keep alive
-    flags = (ST_EPI_SILU if activation else 0) | (ST_EPI_GEGLU if geglu else 0)
+    # weights are parameters, never the output of the kernel launched just before: let the GEMM start
+    # streaming them ahead of the PDL dependency (ST_W_STATIC)
+    flags = (ST_EPI_SILU if activation else 0) | (ST_EPI_GEGLU if geglu else 0) | ST_W_STATIC
     check(L.st_gemm_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), out.data_ptr(), n_out, m, n_rows, k,
                          _ptr(bias), res_ptr, ldr, flags, block_n, _stream(x)), "gemm")
     return out
@@ -380,7 +382,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             wp.permute(0, 2, 3, 1).reshape(k, 9 * c), (0, 0, 0, 8 - k)).contiguous())
         b8 = None if bias is None else _padded(bias, "k8", lambda: torch.nn.functional.pad(bias, (0, 8 - k)).contiguous())
         y8 = torch.empty((n * h * w, 8), dtype=BF16, device=x.device)
-        check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), w8.data_ptr(), _ptr(b8), y8.data_ptr(), n, h, w, c, 8, 0, 0, 0, 0,
+        check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), w8.data_ptr(), _ptr(b8), y8.data_ptr(), n, h, w, c, 8, 0, 0, 0, ST_W_STATIC,
                                      64, stream), "conv_out")
         if not nchw_output:
             return y8.view(n, h, w, 8)[..., :k].permute(0, 3, 1, 2)
@@ -410,7 +412,8 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         residual = _nhwc(residual)
         res_ptr = residual.data_ptr()
     check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), wp.data_ptr(), _ptr(bias), out.data_ptr(), n, h, w, c, k, _ptr(temb),
-                                 temb.stride(0) if temb is not None else 0, res_ptr, 0, block_n, stream), "conv3x3")
+                                 temb.stride(0) if temb is not None else 0, res_ptr, ST_W_STATIC, block_n, stream),
+          "conv3x3")
     return out
 
 
