@@ -11,6 +11,31 @@ namespace st {
 // (128 x N x 16 runs at its N/2 floor with the warp-convergent issue loop) and the fill moves (128 + BLOCK_N) x
 // 128 bytes at min(88 B/clk per SM, 9.6 KB/clk over all CTAs) out of L2; the epilogue costs a few cycles per
 // output column, and tiles are spread over the SMs in waves.  Ties go to the narrower tile.
+static bool cluster_allowed() {
+  static const bool v = [] {
+    // Experimental, opt-in (ST_GEMM_CLUSTER=1).  Measured on B200 (profiles/r01_gemm_trace.txt): correct, and the
+    // 256 x 256 x 16 pair MMA runs at its 128-cycle floor (tools/mmabench2.cu), but at 148 CTAs the main loop only
+    // goes from 664 to 640 cycles per k-block while cluster launch + pair TMEM allocation + two cluster barriers
+    // add ~1.2 k cycles of set-up per launch: 1070 vs 1250 TFLOP/s on the 2048 x 10240 x 1280 GEGLU projection.
+    const char* e = getenv("ST_GEMM_CLUSTER");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
+// CTA pairs (cta_group::2 MMA, each CTA stages half of the weight tile): vertically adjacent tiles must pair up,
+// the half tile must keep the 1024-byte swizzle alignment, and it only pays once the grid is large enough to hit
+// the aggregate L2 feed limit (below ~96 CTAs the 128x256 loop is tensor-pipe bound anyway).
+static bool want_cluster(int M, int n_cols, int block_n, bool geglu) {
+  if (!cluster_allowed()) return false;
+  const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
+  if (mb % 2 != 0) return false;
+  if (geglu ? block_n != 256 : (block_n != 256 && block_n != 192)) return false;
+  const int out_cols = geglu ? block_n / 2 : block_n;
+  const long tiles = (long)mb * ((n_cols + out_cols - 1) / out_cols);
+  return tiles >= 96;
+}
+
 static int choose_block_n(int M, int n_cols, bool geglu, int K) {
   const int sms = device_sm_count();
   const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
@@ -27,8 +52,12 @@ static int choose_block_n(int M, int n_cols, bool geglu, int K) {
     const long tiles = (long)mb * nb;
     const long waves = (tiles + sms - 1) / sms;
     const double ctas = tiles < sms ? (double)tiles : (double)sms;
-    const double fill_rate = 9600.0 / ctas < 88.0 ? 9600.0 / ctas : 88.0;  // bytes per clock per SM
-    const double fill = (128.0 + bn) * 128.0 / fill_rate;
+    const bool cluster = want_cluster(M, n_cols, bn, geglu);
+    const double l2_bytes = 128.0 * 128.0 + (cluster ? 64.0 : 128.0) * bn;  // per CTA and k-block, out of L2
+    const double sm_bytes = cluster ? l2_bytes : (128.0 + bn) * 128.0;      // into one SM
+    const double fill_l2 = l2_bytes / (9600.0 / ctas);
+    const double fill_sm = sm_bytes / 88.0;
+    const double fill = fill_l2 > fill_sm ? fill_l2 : fill_sm;
     const double mma = 2.0 * bn;
     const double tile_cost = (fill > mma ? fill : mma) * (K / 64) + 1500.0 + 10.0 * out_cols;
     const double cost = waves * tile_cost;
@@ -48,11 +77,11 @@ static int gemm_ramp() {
   return v;
 }
 
-template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false>
+template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false, bool kCluster = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
                        cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N, STAGES>;
-  auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu, kStreamK>;
+  using S = GemmSmem<BLOCK_N, STAGES, kCluster>;
+  auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu, kStreamK, kCluster>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -66,8 +95,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const long units = static_cast<long>(tiles) * (p.K / kGemmBlockK);
   const int sms = device_sm_count();
   // stream-K: every CTA must own at least one (tile, k-block) unit -- an owner waits for its successors
-  const int grid = p.stream_k ? static_cast<int>(units < sms ? units : sms) : (tiles < sms ? tiles : sms);
-  launch_kernel(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, ta, tb, td, p);
+  int grid = p.stream_k ? static_cast<int>(units < sms ? units : sms) : (tiles < sms ? tiles : sms);
+  if (kCluster) {  // one cluster per pair of vertically adjacent tiles, at most sms / 2 clusters
+    const int pair_tiles = tiles / 2;
+    grid = 2 * (pair_tiles < sms / 2 ? pair_tiles : sms / 2);
+  }
+  launch_kernel_cluster(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, kCluster ? 2 : 1, ta, tb, td, p);
   ST_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return ST_OK;
 }
@@ -75,6 +108,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 template <bool kConvA>
 static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
                          int block_n, bool geglu, cudaStream_t stream) {
+  if (p.cluster) {
+    if (geglu && block_n == 256) return launch_gemm<256, 6, kConvA, true, false, true>(ta, tb, td, p, stream);
+    if (!geglu && block_n == 256) return launch_gemm<256, 6, kConvA, false, false, true>(ta, tb, td, p, stream);
+    if (!geglu && block_n == 192) return launch_gemm<192, 7, kConvA, false, false, true>(ta, tb, td, p, stream);
+    set_error("gemm: no cluster instantiation for block_n %d", block_n);
+    return ST_ERR_INVALID_ARGUMENT;
+  }
   if (geglu) {
     switch (block_n) {
       case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, td, p, stream);
@@ -191,11 +231,12 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.ramp = gemm_ramp();
   p.ws = sk_ws;
   p.flags = sk_flags;
+  p.cluster = (!stream_k && want_cluster(M, n_out, block_n, geglu)) ? 1 : 0;
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, M, K, lda, kGemmBlockM);
   if (rc != ST_OK) return rc;
-  rc = make_tmap_2d(&tb, W, N, K, ldw, geglu ? block_n / 2 : block_n);
+  rc = make_tmap_2d(&tb, W, N, K, ldw, (geglu || p.cluster) ? block_n / 2 : block_n);  // one box per B load
   if (rc != ST_OK) return rc;
   CUtensorMap td;
   rc = make_tmap_2d(&td, D, M, n_out, ldd, kGemmBlockM);
@@ -266,6 +307,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.ramp = gemm_ramp();
   p.ws = sk_ws;
   p.flags = sk_flags;
+  p.cluster = (!stream_k && want_cluster(N * H * W, K, block_n, false)) ? 1 : 0;
   p.conv_H = H;
   p.conv_W = W;
   p.conv_C = C;
@@ -275,7 +317,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   CUtensorMap ta, tb;
   int rc = make_tmap_nhwc(&ta, x, N, H, W, C, Ht, Wt, Nt);
   if (rc != ST_OK) return rc;
-  rc = make_tmap_2d(&tb, w, K, 9 * (uint64_t)C, 9 * (uint64_t)C, block_n);
+  rc = make_tmap_2d(&tb, w, K, 9 * (uint64_t)C, 9 * (uint64_t)C, p.cluster ? block_n / 2 : block_n);
   if (rc != ST_OK) return rc;
   CUtensorMap td;
   rc = make_tmap_2d(&td, y, M, K, K, kGemmBlockM);

@@ -54,6 +54,7 @@ struct GemmParams {
   int stream_k;
   int ramp;      // debug/tuning: number of k-blocks requested before waiting for the first to land (0 = off)
   int w_static;  // W is not written by the preceding kernel: prefetch it ahead of the PDL wait
+  int cluster;   // host-side choice: launch the two-CTA multicast instantiation
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
   // 4-D (conv) A addressing
@@ -61,10 +62,11 @@ struct GemmParams {
   int conv_Wt, conv_Ht;        // tile rectangle, Wt * Ht == 128
 };
 
-template <int BLOCK_N, int STAGES>
+// kHalfB: CTA-pair mode, each CTA stages only BLOCK_N / 2 rows of the weight tile
+template <int BLOCK_N, int STAGES, bool kHalfB = false>
 struct GemmSmem {
   static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
+  static constexpr int kBBytes = (kHalfB ? BLOCK_N / 2 : BLOCK_N) * kGemmBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutStageBytes = kGemmBlockM * 64 * 2;  // epilogue staging tile for the TMA store
   static constexpr int kBarrierBytes = 1024;
@@ -88,14 +90,22 @@ __device__ __forceinline__ void add_bf16x8(float (&x)[8], const uint4& u) {
 }
 
 // kConvA: A through the 4-D NHWC map.  kGeglu: B tile = [BLOCK_N/2 "state" rows | BLOCK_N/2 "gate" rows].
-template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false>
+// kCluster: CTA pairs (2-CTA clusters, tcgen05 cta_group::2) on vertically adjacent tiles -- same n-block, m-blocks
+// 2i and 2i+1.  One MMA instruction, issued by the even ("leader") CTA, drives both tensor cores on a 256 x
+// BLOCK_N tile; every CTA stages its own 128 rows of A and only HALF of the weight tile (BLOCK_N/2 rows), and
+// each accumulates its 128 output rows in its own TMEM.  Operand fill per CTA and k-block drops from 48 KB to
+// 32 KB (BLOCK_N = 256): at 148 resident CTAs the one-CTA main loop is bound by the ~9.7 KB/clk the L2 can feed
+// all SMs together (757 cycles per k-block against 512 of tensor pipe; profiles/r01_gemm_trace.txt).  A plain
+// TMA multicast of the weight tile (both CTAs still ingest all of it) was measured slower than no cluster.
+template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false, bool kCluster = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
-  using S = GemmSmem<BLOCK_N, STAGES>;
+  using S = GemmSmem<BLOCK_N, STAGES, kCluster>;
   constexpr int kAccCols = BLOCK_N;                       // fp32 accumulator columns per stage
   constexpr int kTmemCols = tmem_cols_for(2 * kAccCols);  // two accumulator stages
   static_assert(2 * kAccCols <= 512, "accumulator stages exceed TMEM");
+  static_assert(!(kStreamK && kCluster), "stream-K and cluster multicast are exclusive");
   static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(!kGeglu || BLOCK_N % 128 == 0, "the TMA store works on 64-column groups of the output tile");
 
@@ -116,6 +126,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_k_blocks = p.K / kGemmBlockK;
   // Work iterator: plain mode = whole tiles blockIdx.x, +gridDim.x, ...; stream-K = one contiguous range of
   // (tile, k-block) units.  A segment is (tile, [kb0, kb1)).
+  const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0;
   const long long sk_units = static_cast<long long>(num_tiles) * num_k_blocks;
   const int sk_u0 = kStreamK ? static_cast<int>(sk_units * blockIdx.x / gridDim.x) : 0;
   const int sk_u1 = kStreamK ? static_cast<int>(sk_units * (blockIdx.x + 1) / gridDim.x) : 0;
@@ -126,6 +137,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       kb0 = cursor - tile * num_k_blocks;
       kb1 = min(num_k_blocks, kb0 + (sk_u1 - cursor));
       cursor += kb1 - kb0;
+    } else if (kCluster) {
+      // the cluster walks pair-tiles (two m-blocks x one n-block); this CTA takes m-block 2*mp + rank
+      const int half_mb = p.num_m_blocks >> 1;
+      if (cursor >= half_mb * p.num_n_blocks) return false;
+      const int nb = cursor / half_mb;
+      tile = nb * p.num_m_blocks + 2 * (cursor - nb * half_mb) + static_cast<int>(cta_rank);
+      kb0 = 0;
+      kb1 = num_k_blocks;
+      cursor += gridDim.x >> 1;
     } else {
       if (cursor >= num_tiles) return false;
       tile = cursor;
@@ -135,7 +155,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     return true;
   };
-  const int cursor0 = kStreamK ? sk_u0 : static_cast<int>(blockIdx.x);
+  const int cursor0 = kStreamK ? sk_u0 : static_cast<int>(kCluster ? blockIdx.x >> 1 : blockIdx.x);
 #define ST_TRACE(slot)                                                      \
   do {                                                                      \
     if (p.trace) p.trace[blockIdx.x * 12 + (slot)] = clock64();              \
@@ -152,15 +172,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kGemmEpiThreads / 32);
+      mbar_init(&tmem_empty[i], (kCluster ? 2 : 1) * kGemmEpiThreads / 32);  // pair: both CTAs' epilogue warps
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (kCluster)
+      tmem_alloc_pair<kTmemCols>(tmem_slot);  // same warp in both CTAs
+    else
+      tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (kCluster) cluster_sync();  // the leader's barriers exist before the peer's first TMA load signals them
   // everything above touched only shared / tensor memory: it may overlap the previous kernel's tail
   pdl_launch_dependents();
   if (warp != 0) pdl_wait();
@@ -169,6 +195,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      // B tile of k-block kb / n-block n_blk into ring slot `sb`.  Pair mode: this CTA fetches only its half of the
+      // rows (GEGLU: rank 0 the "state" rows, rank 1 the "gate" rows); completion is signalled to the leader.
+      constexpr uint32_t kMyStageBytes = S::kStageBytes;
+      auto arm = [&](uint64_t* bar) {  // pair: the leader arms its barrier for both CTAs' bytes
+        if (!kCluster)
+          mbar_expect_tx(bar, kMyStageBytes);
+        else if (cta_rank == 0)
+          mbar_expect_tx(bar, 2 * kMyStageBytes);
+      };
+      auto load_b = [&](uint8_t* sb, uint64_t* bar, int kb, int n_blk) {
+        if (kCluster) {
+          const int r0 = kGeglu ? (cta_rank ? p.n_out : 0) + n_blk * (BLOCK_N / 2)
+                                : n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
+          tma_load_2d_pair(sb, &tmap_b, leader_addr(bar), kb * kGemmBlockK, r0);
+        } else if (kGeglu) {
+          const int h0 = n_blk * (BLOCK_N / 2);
+          tma_load_2d(sb, &tmap_b, bar, kb * kGemmBlockK, h0);
+          tma_load_2d(sb + S::kBBytes / 2, &tmap_b, bar, kb * kGemmBlockK, p.n_out + h0);
+        } else {
+          tma_load_2d(sb, &tmap_b, bar, kb * kGemmBlockK, n_blk * BLOCK_N);
+        }
+      };
       // The weight operand is not produced by the preceding kernel (p.w_static): start its first tiles
       // towards shared memory BEFORE the programmatic dependency resolves, so the HBM latency of the
       // weights (never L2-resident: 5 GB stream per step) hides under the previous kernel's tail.
@@ -177,25 +225,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int cursor = cursor0, tile, kb0, kb1;
         if (next_segment(cursor, tile, kb0, kb1)) {
           const int n_blk = tile / p.num_m_blocks;
-          prefetched = min(p.ramp > 0 ? min(p.ramp, STAGES) : STAGES, kb1 - kb0);
+          prefetched = min((!kCluster && p.ramp > 0) ? min(p.ramp, STAGES) : STAGES, kb1 - kb0);
           for (int i = 0; i < prefetched; ++i) {
             uint8_t* sb = smem_ab + i * S::kStageBytes + S::kABytes;
             const int kb = kb0 + i;
-            mbar_expect_tx(&full_bar[i], S::kStageBytes);
-            if (kGeglu) {
-              const int h0 = n_blk * (BLOCK_N / 2);
-              tma_load_2d(sb, &tmap_b, &full_bar[i], kb * kGemmBlockK, h0);
-              tma_load_2d(sb + S::kBBytes / 2, &tmap_b, &full_bar[i], kb * kGemmBlockK, p.n_out + h0);
-            } else {
-              tma_load_2d(sb, &tmap_b, &full_bar[i], kb * kGemmBlockK, n_blk * BLOCK_N);
-            }
+            arm(&full_bar[i]);
+            load_b(sb, &full_bar[i], kb, n_blk);
           }
         }
       }
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
-      int ramp_left = p.ramp;
+      int ramp_left = kCluster ? 0 : p.ramp;  // (the peer of a pair never sees its own full barriers complete)
       const int cblocks = kConvA ? p.conv_C / kGemmBlockK : 1;
       int cursor = cursor0, tile, kb0, kb1;
       while (next_segment(cursor, tile, kb0, kb1)) {
@@ -218,25 +260,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             --prefetched;
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+            arm(&full_bar[stage]);
           }
           if (kConvA) {
             const int tap = kb / cblocks;
             const int cb = kb - tap * cblocks;
             const int r = tap / 3, s = tap - r * 3;
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * kGemmBlockK, q0 + s - 1, p0 + r - 1, img);
+            if (kCluster)
+              tma_load_4d_pair(sa, &tmap_a, leader_addr(&full_bar[stage]), cb * kGemmBlockK, q0 + s - 1, p0 + r - 1, img);
+            else
+              tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * kGemmBlockK, q0 + s - 1, p0 + r - 1, img);
+          } else if (kCluster) {
+            tma_load_2d_pair(sa, &tmap_a, leader_addr(&full_bar[stage]), kb * kGemmBlockK, m0);
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0);
           }
-          if (b_in_flight) {
-            // weights already on their way
-          } else if (kGeglu) {
-            const int h0 = n_blk * (BLOCK_N / 2);
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, h0);
-            tma_load_2d(sb + S::kBBytes / 2, &tmap_b, &full_bar[stage], kb * kGemmBlockK, p.n_out + h0);
-          } else {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_blk * BLOCK_N);
-          }
+          if (!b_in_flight) load_b(sb, &full_bar[stage], kb, n_blk);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -252,8 +291,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================================== MMA issuer =======================================
     // The whole warp runs this loop (see umma_bf16_ss_elect in ptx.cuh): one elected lane issues, operand
     // descriptors advance by 64-bit adds from a per-kernel base.
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBlockM, BLOCK_N, 0, 0);
+    if (!kCluster || cta_rank == 0) {  // pair: the leader issues for both tensor cores
+      constexpr uint32_t idesc = umma_idesc_bf16(kCluster ? 2 * kGemmBlockM : kGemmBlockM, BLOCK_N, 0, 0);
       const uint64_t desc_a0 = umma_smem_desc_sw128(smem_u32(smem_ab), 0, 1024);
       const uint64_t desc_b0 = umma_smem_desc_sw128(smem_u32(smem_ab) + S::kABytes, 0, 1024);
       constexpr uint32_t kStageStep = S::kStageBytes >> 4;  // descriptor address field counts 16-byte units
@@ -275,14 +314,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint64_t db = desc_b0 + static_cast<uint64_t>(stage * kStageStep);
 #pragma unroll
           for (int k = 0; k < kGemmBlockK / 16; ++k)  // +32 bytes of K per instruction = +2 address units
-            umma_bf16_ss_elect(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
-          umma_commit_elect(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (kCluster)
+              umma_bf16_ss_pair_elect(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+            else
+              umma_bf16_ss_elect(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+          // smem slot reusable once these MMAs retire (pair: in both CTAs' rings)
+          if (kCluster)
+            umma_commit_pair_elect(&empty_bar[stage], 0x3);
+          else
+            umma_commit_elect(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_elect(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (kCluster)  // accumulator complete -> both CTAs' epilogues
+          umma_commit_pair_elect(&tmem_full[acc], 0x3);
+        else
+          umma_commit_elect(&tmem_full[acc]);
         if (first_seg && lane == 0) ST_TRACE(3);
         first_seg = false;
         if (++acc == 2) {
@@ -515,7 +564,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
       if (first_seg && warp == 2 && lane == 0) ST_TRACE(5);
       first_seg = false;
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (kCluster)
+          mbar_arrive_cluster(leader_addr(&tmem_empty[acc]));  // the leader's MMA warp owns the accumulator hand-off
+        else
+          mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -527,7 +581,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  if (kCluster) {
+    // the leader's MMAs read the peer's ring and its commits signal the peer's barriers: nobody leaves (or frees
+    // tensor memory) before both CTAs are done
+    cluster_sync();
+    if (warp == 1) tmem_dealloc_pair<kTmemCols>(tmem_base);
+  } else if (warp == 1) {
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
   if (threadIdx.x == 0) ST_TRACE(6);
 #undef ST_TRACE
 }
