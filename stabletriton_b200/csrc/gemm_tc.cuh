@@ -54,7 +54,8 @@ struct GemmParams {
   int stream_k;
   int ramp;      // debug/tuning: number of k-blocks requested before waiting for the first to land (0 = off)
   int w_static;  // W is not written by the preceding kernel: prefetch it ahead of the PDL wait
-  int cluster;   // host-side choice: launch the two-CTA multicast instantiation
+  int cluster;   // host-side choice: launch the CTA-pair instantiation
+  int l2_prefetch, l2_prefetch_mod;  // weight-tile L2 prefetch distance (k-blocks, 0 = off) and issuing m-block stride
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
   // 4-D (conv) A addressing
@@ -276,6 +277,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0);
           }
           if (!b_in_flight) load_b(sb, &full_bar[stage], kb, n_blk);
+          // Weights are read once per step, so every B tile of the main loop is an HBM miss for the CTAs that
+          // share it (they run in lock step); the 4-stage ring only covers an L2-hit latency.  Ask L2 for the
+          // tile p.l2_prefetch k-blocks ahead (one CTA in p.l2_prefetch_mod per n-block does the asking).
+          if (p.l2_prefetch > 0 && (m_blk % p.l2_prefetch_mod) == 0 && kb + p.l2_prefetch < kb1) {
+            const int kp = (kb + p.l2_prefetch) * kGemmBlockK;
+            if (kGeglu) {
+              tma_prefetch_l2_2d(&tmap_b, kp, n_blk * (BLOCK_N / 2));
+              tma_prefetch_l2_2d(&tmap_b, kp, p.n_out + n_blk * (BLOCK_N / 2));
+            } else if (kCluster) {
+              tma_prefetch_l2_2d(&tmap_b, kp, n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2));
+            } else {
+              tma_prefetch_l2_2d(&tmap_b, kp, n_blk * BLOCK_N);
+            }
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
