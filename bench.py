@@ -311,8 +311,11 @@ def run_gpu_arm(args):
         ms_step = ms_total / steps
         roofline = {
             "bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all Linear + conv launches of one step)",
+            "traffic_note": "dram read+write bytes per launch, mean over the 495 launches of one step, from the committed "
+                            "ncu capture profiles/r01_ncu_launch_summary_v3.json (ncu flushes L2 before every launch, so "
+                            "activations are counted as DRAM reads: 5.1 GB of weights + 6.4 GB of activations per step)",
             "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+            "frac": achieved / peaks["tflops_sustained"], "traffic": ncu_gemm_traffic_per_launch(),
             "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "launches_per_step": len(gemm_calls),
             "flops_per_step": fam_flops, "ms_per_step_in_kernel": fam_ms, "share_of_step": fam_ms / ms_step,
             "whole_step_frac_of_roofline": (FLOPS_CONFIG2 * prompts / peaks["tflops_sustained"] / 1e12
@@ -355,6 +358,17 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_gemm_traffic_per_launch():
+    """DRAM bytes per GEMM launch from the committed ncu launch list (profiles/), or None if it is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_launch_summary_v3.json")
+    try:
+        with open(path) as f:
+            fam = json.load(f)["families"]["gemm_bf16_tc_kernel"]
+        return (fam["dram_read_bytes"] + fam["dram_write_bytes"]) / fam["launches"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def main():

@@ -1,16 +1,18 @@
-// Flash attention forward for head_dim 64 on sm_100a: TMA-fed tcgen05 tiles, S, P and the per-block
-// P.V product all in TMEM, online softmax in fp32 registers (one thread per query row, so row max /
-// sum need no shuffles).
+// Flash attention forward for head_dim 64 on sm_100a: TMA-fed tcgen05 tiles, S, P and O in TMEM, softmax in
+// fp32 registers.  Two kernels behind st_attention_bf16:
 //
-//   grid = (ceil(Tq / 128), B * H); 320 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-//   warps 2..9 softmax / accumulate / store (two warps per TMEM lane quadrant, each owning half of every
-//   row).  Two CTAs are resident per SM (<= 84 KB smem, 256 TMEM columns, <= 85 registers), so while one
-//   CTA's softmax warps sit on the MUFU pipe the other CTA's MMAs keep the tensor pipe busy.
+//   attn_fwd_kernel            Tk <= 128 (the 77-token cross attention: one K/V block, nothing to pipeline).
+//   attn_fwd_pipelined_kernel  Tk  > 128 (self attention): one CTA per SM, double-buffered S / P, O accumulated in
+//                              TMEM, max / exp warp specialisation, lazy rescale -- see the comment above it.
+//
+// attn_fwd_kernel: grid = (ceil(Tq / 128), B * H); 320 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM
+//   owner, warps 2..9 softmax / accumulate / store (two warps per TMEM lane quadrant, each owning half of every
+//   row).  Two CTAs are resident per SM (<= 84 KB smem, 256 TMEM columns, <= 85 registers).
 //
 //   S = Q K^T        : tcgen05.mma SS (Q, K 128B-swizzled K-major tiles from TMA), 128 fp32 columns
 //   P = 2^(S*c - m)  : written back to TMEM as packed bf16 (64 columns) with tcgen05.st
-//   O_j = P V        : tcgen05.mma TS -- A operand straight from TMEM, V as an MN-major smem operand --
-//                      ~4x cheaper than the SS form (a 128x64x16 SS MMA is bound by the smem A fetch)
+//   O_j = P V        : tcgen05.mma TS -- A operand straight from TMEM, V as an MN-major smem operand (32 cycles per
+//                      128 x 64 x 16 instruction against 48 for the SS form; tools/mmabench.cu)
 //   O += O_j         : folded into fp32 registers one block late, rescaled by 2^(m_old - m_new)
 //
 // Semantics = the *pattern* of fuse_attention (reference: optimizers/replace_attention.py:76-86;

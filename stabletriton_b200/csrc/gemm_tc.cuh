@@ -8,14 +8,14 @@
 // (tmem_full/tmem_empty, MMA <-> epilogue) and a static persistent tile schedule (tile = blockIdx.x +
 // i * gridDim.x), so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-// Measured on B200 (profiles/r01_gemm_trace.txt): with both operands in shared memory a
-// 128 x N x 16 tcgen05.mma costs ~128 cycles for every N <= 256 (the 4 KB A-slice read bounds it), so
-// only wide tiles reach the tensor peak -- the launcher prefers BLOCK_N = 256.  The epilogue therefore
-// has to stay off the critical path: the per-tile bias (+ per-image time-embedding row) is staged
-// once in shared memory, the residual rows are prefetched into registers *before* the accumulator is
-// waited for, and the bf16 result leaves through a swizzled staging tile and TMA bulk stores
-// (64 columns x 128 rows each, clipped at the matrix edge by the tensor map), so no global-memory
-// round trip and no uncoalesced store sits between TMEM and HBM.
+// Measured on B200 (profiles/r01_gemm_trace.txt, tools/mmabench.cu): issued from a warp-convergent loop (see
+// umma_bf16_ss_elect) a 128 x N x 16 tcgen05.mma runs at N/2 cycles, so a 128 x 256 k-block needs 512 cycles of
+// tensor pipe and 48 KB of operand fill; at 148 resident CTAs the fill (~9.7 KB/clk out of L2 for all SMs) is the
+// bound (664 cycles).  The epilogue therefore has to stay off the critical path: the per-tile bias (+ per-image
+// time-embedding row) is staged once in shared memory, the residual rows are prefetched into registers *before*
+// the accumulator is waited for, and the bf16 result leaves through a swizzled staging tile and TMA bulk stores
+// (64 columns x 128 rows each, clipped at the matrix edge by the tensor map), so no global-memory round trip and
+// no uncoalesced store sits between TMEM and HBM.
 //
 // A is fetched either through a 2-D tensor map (plain GEMM: Linear, 1x1 conv, im2col'ed conv) or a
 // 4-D NHWC tensor map (3x3 / pad 1 / stride 1 convolution): the 128 output pixels of a tile form a
