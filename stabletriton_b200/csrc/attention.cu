@@ -47,6 +47,7 @@ struct AttnParams {
 
 // Registers are allocated per group of 4 warps: the 10 warps of this CTA cost as much as 12, so two resident
 // CTAs need <= 85 registers per thread -- hence the bound of 384 threads although 320 are launched.
+template <bool kTrace>
 __global__ void __launch_bounds__(384, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -73,9 +74,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int b = blockIdx.y / p.H;
   const int h = blockIdx.y - b * p.H;
   const int nkv = (p.Tk + kAttnBlockKV - 1) / kAttnBlockKV;
-#define AT_TRACE(slot)                                                                  \
-  do {                                                                                  \
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[slot] = clock64();       \
+#define AT_TRACE(slot)                                                                        \
+  do {                                                                                        \
+    if (kTrace && p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[slot] = clock64();   \
   } while (0)
   if (threadIdx.x == 0) AT_TRACE(0);
 
@@ -326,6 +327,7 @@ constexpr int kA3SmemBytes = kAttnTileBytes * (1 + 2 * kA3Stages) + 256 + 2048 +
 constexpr int kA3TmemCols = 512;
 constexpr float kA3Tau = 8.f;  // log2 units
 
+template <bool kTrace>
 __global__ void __launch_bounds__(kA3Threads, 1)
 attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -528,20 +530,45 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       }
     }
 
+    // S(j) arrives in two 32-column chunks per thread (va, vb).  While the second chunk of block j is being
+    // exponentiated, the first chunk of block j+1 is already requested (its reference is normally published a
+    // block ahead), so the barrier / shared-memory / TMEM latencies at a block boundary hide under the MUFU stream.
+    // Likewise P(j) is only published (tcgen05.wait::st + arrive) after the first chunk of block j+1 has been
+    // exponentiated: by then the stores have long landed, so the wait costs nothing, and P(j).V(j) is not on the
+    // critical path (the tensor pipe is idle two thirds of the time).
+    uint32_t va[32], vb[32];
+    bool pre = false;   // va already holds (a request for) the first chunk of the next block; warp-uniform
+    float m_pre = 0.f;
+    int unpublished = -1;  // block whose P stores are issued but not yet published
+    auto publish = [&]() {
+      if (unpublished >= 0) {
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[unpublished & 1]);
+        unpublished = -1;
+      }
+    };
     for (int j = 0; j < nkv; ++j) {
       const int buf = j & 1;
       const int valid = p.Tk - j * kAttnBlockKV - half * 64;  // my columns >= valid are padding
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(1);
       if (j == nkv - 1 && warp == 2 && lane == 0) AT_TRACE(10);
-      // the max warps arrive on m_ready(j) after they have seen s_full(j): S(j) is complete
-      mbar_wait(&m_ready[buf], (j >> 1) & 1);
-      tc_fence_after();
       const uint32_t t_s = tmem_S + buf * 128 + lane_off + half * 64;
       const uint32_t t_p = tmem_P + buf * 64 + lane_off + half * 32;
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32b_x32(t_s, va);
+      float m;
+      if (!pre) {
+        // about to block: publish P(j-1) first -- the max warps may need P(j-1).V(j-1) (a reference move rescales O
+        // after it) before they publish m(j)
+        publish();
+        // the max warps arrive on m_ready(j) after they have seen s_full(j): S(j) is complete
+        mbar_wait(&m_ready[buf], (j >> 1) & 1);
+        tc_fence_after();
+        tmem_ld_32x32b_x32(t_s, va);
+        m = s_m[buf * 128 + row];
+      } else {
+        m = m_pre;
+      }
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(2);
-      const float m = s_m[buf * 128 + row];
       if (m != m_prev) {
         l *= ex2_approx(m_prev - m);  // first block: l = 0 and 2^(-inf) = 0
         m_prev = m;
@@ -558,6 +585,16 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
           // all of my S(j) is in registers: the MMA warp may overwrite this S buffer with S(j+2)
           tc_fence_before();
           mbar_arrive(&s_free[buf]);
+          pre = false;
+          if (j + 1 < nkv) {
+            const bool ok = mbar_test_wait(&m_ready[buf ^ 1], ((j + 1) >> 1) & 1);  // a poll, never a suspend
+            if (__all_sync(0xffffffffu, ok)) {  // tcgen05.ld is warp-collective: decide as a warp
+              tc_fence_after();
+              tmem_ld_32x32b_x32(tmem_S + (buf ^ 1) * 128 + lane_off + half * 64, va);
+              m_pre = s_m[(buf ^ 1) * 128 + row];
+              pre = true;
+            }
+          }
         }
         if (c + 32 > valid) {
 #pragma unroll
@@ -578,20 +615,21 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
           pk[(i >> 1) + 0] = pack_bf16x2(e0, e1);
           pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
         }
-        if (c == 0 && j >= 2) {  // P buffer `buf` was last read by P(j-2) V(j-2), issued a whole block ago
-          mbar_wait(&pv_done[buf], ((j >> 1) - 1) & 1);
-          tc_fence_after();
+        if (c == 0) {
+          publish();  // P(j-1): its stores were issued >= 512 MUFU cycles ago
+          if (j >= 2) {  // P buffer `buf` was last read by P(j-2) V(j-2)
+            mbar_wait(&pv_done[buf], ((j >> 1) - 1) & 1);
+            tc_fence_after();
+          }
         }
         tmem_st_32x32b_x16(t_p + (c >> 1), pk);
         if (c == 0) tmem_ld_wait();
       }
       l += (rs0 + rs1) + (rs2 + rs3);
+      unpublished = j;
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(6);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[buf]);
-      if (j == 2 && warp == 2 && lane == 0) AT_TRACE(7);
     }
+    publish();
     float acc[32];
     {
       mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
@@ -691,15 +729,20 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   if (rc != ST_OK) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
     }
     // two CTAs per SM need 2 x 82 KB: ask for the largest shared-memory carve-out
-    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
+    cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
@@ -718,7 +761,7 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   p.trace = g_attn_trace;
   static const int skew = [] {
     const char* e = getenv("ST_ATTN_SKEW");
-    return e ? atoi(e) : 600;
+    return e ? atoi(e) : 0;
   }();
   p.skew = skew;
   const dim3 grid((Tq + kAttnBlockQ - 1) / kAttnBlockQ, B * H);
@@ -728,13 +771,14 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
     return !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : 0));
   }();
   const bool pipelined = force ? force == 2 : Tk > kAttnBlockKV;
+  const bool trace = p.trace != nullptr;  // the phase stamps are compiled out of the production instantiations
   if (pipelined) {
-    launch_kernel(attn_fwd_pipelined_kernel, dim3(grid), dim3(kA3Threads), kA3SmemBytes,
-                  static_cast<cudaStream_t>(stream), tq, tk, tv, p);
+    launch_kernel(trace ? attn_fwd_pipelined_kernel<true> : attn_fwd_pipelined_kernel<false>, dim3(grid),
+                  dim3(kA3Threads), kA3SmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
   } else {
-    launch_kernel(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes, static_cast<cudaStream_t>(stream), tq,
-                  tk, tv, p);
+    launch_kernel(trace ? attn_fwd_kernel<true> : attn_fwd_kernel<false>, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes,
+                  static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_kernel");
   }
   return ST_OK;
@@ -745,15 +789,15 @@ void st_debug_set_attention_trace(void* buf) { st::g_attn_trace = static_cast<un
 // Debug hook: resident CTAs per SM the driver grants the attention kernel (2 expected).
 int st_debug_attention_occupancy(void) {
   int n = -1;
-  cudaFuncSetAttribute(st::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kAttnSmemBytes);
-  cudaFuncSetAttribute(st::attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+  cudaFuncSetAttribute(st::attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kAttnSmemBytes);
+  cudaFuncSetAttribute(st::attn_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                        cudaSharedmemCarveoutMaxShared);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, st::attn_fwd_kernel, st::kAttnThreads, st::kAttnSmemBytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, st::attn_fwd_kernel<false>, st::kAttnThreads, st::kAttnSmemBytes);
   cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, st::attn_fwd_kernel);
+  cudaFuncGetAttributes(&fa, st::attn_fwd_kernel<false>);
   int n48 = -1, n0 = -1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n48, st::attn_fwd_kernel, st::kAttnThreads, 48 * 1024);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, st::attn_fwd_kernel, st::kAttnThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n48, st::attn_fwd_kernel<false>, st::kAttnThreads, 48 * 1024);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, st::attn_fwd_kernel<false>, st::kAttnThreads, 0);
   printf("attn kernel: regs %d, static smem %zu, max dyn smem %d, local %zu, occupancy @%d B: %d, @48K: %d, @0: %d\n",
          fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, st::kAttnSmemBytes, n, n48, n0);
   return n;

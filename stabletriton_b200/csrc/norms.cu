@@ -197,41 +197,47 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   __threadfence();
   for (int g = warp < warps ? warp : G; g < G; g += warps) {
     const float* q = partial + ((static_cast<size_t>(n) * G + g) * 3) * chunks;
-    // every lane fetches all of its chunk triples before reducing: one L2 round trip per group, not 2*chunks/32
-    constexpr int kPer = 8;  // covers 256 chunks per pass
+    // every lane fetches ALL of its chunk triples up front and keeps them: one L2 round trip per group (the
+    // first version made two -- means, then M2 -- and this serial tail was the longest part of the kernel)
+    constexpr int kPer = 8;  // 256 chunks per pass; gn_geometry never makes more than ~3 x SMs / N
     float nsum = 0.f, wsum = 0.f, m2 = 0.f;
-    for (int k0 = 0; k0 < chunks; k0 += 32 * kPer) {  // (a second pass only beyond 256 chunks)
-      float nk[kPer], mk[kPer];
+    if (chunks <= 32 * kPer) {
+      float nk[kPer], mk[kPer], qk[kPer];
 #pragma unroll
       for (int i = 0; i < kPer; ++i) {
-        const int k = k0 + lane + 32 * i;
+        const int k = lane + 32 * i;
         nk[i] = k < chunks ? __ldcg(q + k) : 0.f;
         mk[i] = k < chunks ? __ldcg(q + chunks + k) : 0.f;
+        qk[i] = k < chunks ? __ldcg(q + 2 * chunks + k) : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < kPer; ++i) {
         nsum += nk[i];
         wsum = fmaf(nk[i], mk[i], wsum);
       }
-    }
-    nsum = warp_sum(nsum);
-    wsum = warp_sum(wsum);
-    const float mean = wsum / nsum;
-    for (int k0 = 0; k0 < chunks; k0 += 32 * kPer) {
-      float nk[kPer], mk[kPer], qk[kPer];
+      nsum = warp_sum(nsum);
+      wsum = warp_sum(wsum);
+      const float mean0 = wsum / nsum;
 #pragma unroll
       for (int i = 0; i < kPer; ++i) {
-        const int k = k0 + lane + 32 * i;
-        nk[i] = k < chunks ? __ldcg(q + k) : 0.f;
-        mk[i] = k < chunks ? __ldcg(q + chunks + k) : mean;
-        qk[i] = k < chunks ? __ldcg(q + 2 * chunks + k) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < kPer; ++i) {
-        const float d = mk[i] - mean;
+        const float d = mk[i] - mean0;  // padded lanes: nk = qk = 0, so d does not matter
         m2 += qk[i] + nk[i] * d * d;
       }
+    } else {
+      for (int k = lane; k < chunks; k += 32) {
+        const float nk = __ldcg(q + k);
+        nsum += nk;
+        wsum = fmaf(nk, __ldcg(q + chunks + k), wsum);
+      }
+      nsum = warp_sum(nsum);
+      wsum = warp_sum(wsum);
+      const float mean0 = wsum / nsum;
+      for (int k = lane; k < chunks; k += 32) {
+        const float d = __ldcg(q + chunks + k) - mean0;
+        m2 += __ldcg(q + 2 * chunks + k) + __ldcg(q + k) * d * d;
+      }
     }
+    const float mean = wsum / nsum;
     m2 = warp_sum(m2);
     const float rstd = rsqrtf(m2 / nsum + eps);  // biased variance, as torch.nn.GroupNorm
     for (int c = lane; c < cpg; c += 32) {
