@@ -316,7 +316,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 //               multiplies O (in TMEM) by 2^(m_old - m_new) -- rare after the first blocks -- so there is no
 //               per-block read-modify-write of O at all.
 //
-//   TMEM   S0 [0,128)  S1 [128,256)  P0 [256,320)  P1 [320,384)  O [384,448)
+//   TMEM   S0 [0,128)  S1 [128,256)  P0 [256,320)  P1 [320,384)  P2 [384,448)  O [448,512)
 //
 // Per 128x128 block the tensor pipe needs 512 cycles (4 x 64 + 8 x 32), the MUFU pipe 1024 (16 ex2/clk/SM);
 // the two-CTA kernel above spends ~2.7 k cycles per block and SM because each CTA's MMA -> max -> exp -> MMA
@@ -344,8 +344,8 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   uint64_t* v_empty = v_full + kA3Stages;
   uint64_t* s_full = v_empty + kA3Stages;  // [2]
   uint64_t* m_ready = s_full + 2;          // [2]
-  uint64_t* p_full = m_ready + 2;          // [2]
-  uint64_t* pv_done = p_full + 2;          // [2]
+  uint64_t* p_full = m_ready + 2;          // [3]
+  uint64_t* pv_done = p_full + 3;          // [2]
   uint64_t* s_free = pv_done + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
   float* s_m = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 buffers][128 rows] references
@@ -373,10 +373,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&m_ready[i], 128);
-      mbar_init(&p_full[i], 256);
       mbar_init(&pv_done[i], 1);
       mbar_init(&s_free[i], 256);
     }
+    for (int i = 0; i < 3; ++i) mbar_init(&p_full[i], 256);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<kA3TmemCols>(tmem_slot);
@@ -387,8 +387,8 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t tmem_S = tmem_base;        // + 128 * (j & 1)
-  const uint32_t tmem_P = tmem_base + 256;  // + 64 * (j & 1)
-  const uint32_t tmem_O = tmem_base + 384;
+  const uint32_t tmem_P = tmem_base + 256;  // + 64 * (j % 3)
+  const uint32_t tmem_O = tmem_base + 448;
   const int quad = warp & 3;                // TMEM lane quadrant this warp may touch
   const int row = quad * 32 + lane;
   const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -442,12 +442,12 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
           tc_fence_after();
           issue_s(j + 2);
         }
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&p_full[j % 3], (j / 3) & 1);
         if (j == 2 && lane == 0) AT_TRACE(8);
         mbar_wait(&v_full[st], (j / kA3Stages) & 1);
         tc_fence_after();
         const uint64_t dv = desc_v0 + static_cast<uint64_t>(st * kTileStep);
-        const uint32_t a = tmem_P + (j & 1) * 64;
+        const uint32_t a = tmem_P + (j % 3) * 64;
 #pragma unroll
         for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)
           umma_bf16_ts_elect(tmem_O, a + kk * 8, dv + 128 * kk, idesc_o, (j > 0) || (kk != 0));
@@ -465,29 +465,28 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t t_s = tmem_S + buf * 128 + lane_off;
+      // two 64-column loads, one TMEM round trip each (four 32-column loads took ~900 cycles per block, and this
+      // warp's S -> reference latency is on the per-block critical chain s_free -> S -> max -> m_ready)
       float mx = -INFINITY;
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32b_x32(t_s, va);
-      tmem_ld_wait();
+      uint32_t v[64];
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t(&cur)[32] = ((c >> 5) & 1) ? vb : va;
-        uint32_t(&nxt)[32] = ((c >> 5) & 1) ? va : vb;
-        if (c + 32 < 128) tmem_ld_32x32b_x32(t_s + c + 32, nxt);
-        if (c + 32 > valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i >= valid) cur[i] = 0xff800000u;  // -inf
-        }
-        float g[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float a0 = max3f(__uint_as_float(cur[8 * q + 0]), __uint_as_float(cur[8 * q + 1]), __uint_as_float(cur[8 * q + 2]));
-          const float a1 = max3f(__uint_as_float(cur[8 * q + 3]), __uint_as_float(cur[8 * q + 4]), __uint_as_float(cur[8 * q + 5]));
-          g[q] = max3f(a0, a1, fmaxf(__uint_as_float(cur[8 * q + 6]), __uint_as_float(cur[8 * q + 7])));
-        }
-        mx = max3f(mx, max3f(g[0], g[1], g[2]), g[3]);
+      for (int c = 0; c < 128; c += 64) {
+        tmem_ld_32x32b_x64(t_s + c, v);
         tmem_ld_wait();
+        if (c + 64 > valid) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (c + i >= valid) v[i] = 0xff800000u;  // -inf
+        }
+        float g[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a0 = max3f(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]), __uint_as_float(v[8 * q + 2]));
+          const float a1 = max3f(__uint_as_float(v[8 * q + 3]), __uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+          g[q] = max3f(a0, a1, fmaxf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+        }
+        mx = max3f(mx, max3f(g[0], g[1], g[2]), max3f(g[3], g[4], g[5]));
+        mx = max3f(mx, g[6], g[7]);
       }
       const float mj = mx * p.scale_log2;  // scale > 0 commutes with max
       const bool move = mj > m + kA3Tau;   // always true on the first block (m = -inf)
@@ -512,6 +511,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       s_m[buf * 128 + row] = m;
       tc_fence_before();
       if (j == 2 && warp == 10 && lane == 0) AT_TRACE(12);
+      if ((j == 16 || j == 17) && lane == 0) AT_TRACE(16 * (j - 15) + 8 + warp - 10);
       if (j == 3 && warp == 10 && lane == 0) AT_TRACE(13);
       mbar_arrive(&m_ready[buf]);  // release: the exp warps' wait acquires s_m and orders the O rescale before P(j)
     }
@@ -533,33 +533,21 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     // S(j) arrives in two 32-column chunks per thread (va, vb).  While the second chunk of block j is being
     // exponentiated, the first chunk of block j+1 is already requested (its reference is normally published a
     // block ahead), so the barrier / shared-memory / TMEM latencies at a block boundary hide under the MUFU stream.
-    // Likewise P(j) is only published (tcgen05.wait::st + arrive) after the first chunk of block j+1 has been
-    // exponentiated: by then the stores have long landed, so the wait costs nothing, and P(j).V(j) is not on the
-    // critical path (the tensor pipe is idle two thirds of the time).
     uint32_t va[32], vb[32];
     bool pre = false;   // va already holds (a request for) the first chunk of the next block; warp-uniform
     float m_pre = 0.f;
-    int unpublished = -1;  // block whose P stores are issued but not yet published
-    auto publish = [&]() {
-      if (unpublished >= 0) {
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[unpublished & 1]);
-        unpublished = -1;
-      }
-    };
     for (int j = 0; j < nkv; ++j) {
       const int buf = j & 1;
       const int valid = p.Tk - j * kAttnBlockKV - half * 64;  // my columns >= valid are padding
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(1);
       if (j == nkv - 1 && warp == 2 && lane == 0) AT_TRACE(10);
+      if ((j == 16 || j == 17) && lane == 0) AT_TRACE(16 * (j - 15) + warp - 2);  // per-warp block period / skew
       const uint32_t t_s = tmem_S + buf * 128 + lane_off + half * 64;
-      const uint32_t t_p = tmem_P + buf * 64 + lane_off + half * 32;
+      // P is triple-buffered: P(j) overwrites P(j-3), and P(j-3).V(j-3) was issued before S(j), whose commit the
+      // max warps saw before publishing m(j) -- so knowing m(j) proves the buffer is free, no barrier to poll
+      const uint32_t t_p = tmem_P + (j % 3) * 64 + lane_off + half * 32;
       float m;
       if (!pre) {
-        // about to block: publish P(j-1) first -- the max warps may need P(j-1).V(j-1) (a reference move rescales O
-        // after it) before they publish m(j)
-        publish();
         // the max warps arrive on m_ready(j) after they have seen s_full(j): S(j) is complete
         mbar_wait(&m_ready[buf], (j >> 1) & 1);
         tc_fence_after();
@@ -574,17 +562,17 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         m_prev = m;
       }
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(3);
+      const bool tr = kTrace && j == 16 && warp == 2 && lane == 0;  // detailed timeline of one steady-state block
+      if (tr) AT_TRACE(48);
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
       tmem_ld_wait();
+      if (tr) AT_TRACE(49);
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         uint32_t(&cur)[32] = ((c >> 5) & 1) ? vb : va;
         if (c == 0) {
           tmem_ld_32x32b_x32(t_s + 32, vb);
         } else {
-          // all of my S(j) is in registers: the MMA warp may overwrite this S buffer with S(j+2)
-          tc_fence_before();
-          mbar_arrive(&s_free[buf]);
           pre = false;
           if (j + 1 < nkv) {
             const bool ok = mbar_test_wait(&m_ready[buf ^ 1], ((j + 1) >> 1) & 1);  // a poll, never a suspend
@@ -601,35 +589,49 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
           for (int i = 0; i < 32; ++i)
             if (c + i >= valid) cur[i] = 0xff800000u;  // -inf -> fma(-inf, c, -m) = -inf -> 2^(-inf) = 0
         }
+        // All 32 exponentials first, back to back, THEN the sums and the bf16 packs: with F2FP / FADD placed right
+        // behind their MUFUs (what the compiler does on its own) the in-order warp waits out the MUFU latency for
+        // every pair -- 22 cycles per element, independent of what the sibling warp does (measured).
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = ex2_approx_ordered(fmaf(__uint_as_float(cur[i]), p.scale_log2, -m));
+        if (c == 0) {
+          // the second chunk has landed by now: all of my S(j) is in registers, and the sooner the MMA warp may
+          // overwrite this S buffer with S(j+2), the sooner the max warps get to publish m(j+2)
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&s_free[buf]);
+        }
+#pragma unroll
+        for (int i = 16; i < 32; ++i) e[i] = ex2_approx_ordered(fmaf(__uint_as_float(cur[i]), p.scale_log2, -m));
+        ready16(e, 0);
+        ready16(e, 16);
+        if (tr) AT_TRACE(c == 0 ? 50 : 55);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(cur[i + 0]), p.scale_log2, -m));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2, -m));
-          const float e2 = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), p.scale_log2, -m));
-          const float e3 = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), p.scale_log2, -m));
-          rs0 += e0;
-          rs1 += e1;
-          rs2 += e2;
-          rs3 += e3;
-          pk[(i >> 1) + 0] = pack_bf16x2(e0, e1);
-          pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
+          rs0 += e[i + 0];
+          rs1 += e[i + 1];
+          rs2 += e[i + 2];
+          rs3 += e[i + 3];
+          pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
+          pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
         }
-        if (c == 0) {
-          publish();  // P(j-1): its stores were issued >= 512 MUFU cycles ago
-          if (j >= 2) {  // P buffer `buf` was last read by P(j-2) V(j-2)
-            mbar_wait(&pv_done[buf], ((j >> 1) - 1) & 1);
-            tc_fence_after();
-          }
-        }
+        if (tr && c == 0) AT_TRACE(51);
         tmem_st_32x32b_x16(t_p + (c >> 1), pk);
-        if (c == 0) tmem_ld_wait();
+        if (tr && c == 0) AT_TRACE(57);
+        if (tr) AT_TRACE(c == 0 ? 54 : 56);
       }
       l += (rs0 + rs1) + (rs2 + rs3);
-      unpublished = j;
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(6);
+      // Publish right away: P(j).V(j) then runs under the next block's first ex2 phase, when these warps do not
+      // touch TMEM.  (Publishing later -- after that phase -- was measured: the tcgen05.st of the next chunk then
+      // queues behind the running MMA for ~250 cycles.)
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[j % 3]);
+      if (tr) AT_TRACE(52);
     }
-    publish();
     float acc[32];
     {
       mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);

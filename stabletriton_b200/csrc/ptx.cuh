@@ -76,6 +76,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Busy poll.  mbar_wait (try_wait) lets the hardware suspend the thread, and a suspended waiter is woken ~300 cycles
+// after the phase completes (measured in the attention pipeline, where three such hand-offs sat on the per-block
+// critical path).  For waits that are latency critical and whose warp has nothing else to do.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_test_wait(bar, parity)) {
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // proxy / tcgen05 fences
 // ------------------------------------------------------------------------------------------------
@@ -345,6 +353,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -407,6 +423,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// volatile form: keeps its program order relative to other volatile asm (see the attention exp loop, where the
+// compiler otherwise puts every F2FP right behind its two MUFUs and the in-order warp eats the MUFU latency per pair)
+__device__ __forceinline__ float ex2_approx_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// scheduling fence for 16 registers: everything that consumes them is issued after everything that produced them
+__device__ __forceinline__ void ready16(float (&e)[32], int o) {
+  asm volatile("" : "+f"(e[o + 0]), "+f"(e[o + 1]), "+f"(e[o + 2]), "+f"(e[o + 3]), "+f"(e[o + 4]), "+f"(e[o + 5]),
+                    "+f"(e[o + 6]), "+f"(e[o + 7]), "+f"(e[o + 8]), "+f"(e[o + 9]), "+f"(e[o + 10]), "+f"(e[o + 11]),
+                    "+f"(e[o + 12]), "+f"(e[o + 13]), "+f"(e[o + 14]), "+f"(e[o + 15]));
 }
 // x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU.TANH (max relative error 2^-11, far below bf16
 // rounding) + two FMA-pipe instructions.  The exp/divide form costs ~12 instructions per element, which made

@@ -728,12 +728,12 @@ int main(int argc, char** argv) {
   }
   if (!strcmp(what, "attn1") && argc >= 6) {  // selftest attn1 B H Tq Tk
     unsigned long long* tr;
-    CK(cudaMalloc(&tr, 16 * 8));
-    CK(cudaMemset(tr, 0, 16 * 8));
+    CK(cudaMalloc(&tr, 64 * 8));
+    CK(cudaMemset(tr, 0, 64 * 8));
     st_debug_set_attention_trace(tr);
     test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, false);
     st_debug_set_attention_trace(nullptr);
-    unsigned long long h[16];
+    unsigned long long h[64];
     CK(cudaMemcpy(h, tr, sizeof h, cudaMemcpyDeviceToHost));
     // slot meanings for the pipelined kernel (Tk > 128); the two-CTA kernel fills 1..9 with its own phases
     const char* nm[14] = {"cta start", "exp warp, block 2: before m_ready wait", "m_ready seen, first S chunk requested",
@@ -742,6 +742,16 @@ int main(int argc, char** argv) {
                           "cta exit", "max warp: m(2) published", "max warp: m(3) published"};
     for (int i = 1; i < 14; ++i)
       if (h[i]) printf("  %-42s %8lld\n", nm[i], (long long)(h[i] - h[0]));
+    if (h[16]) {
+      printf("  block 16 / 17 start per exp warp (2..9), m(16) / m(17) published per max warp (10..13):\n   ");
+      for (int i = 0; i < 12; ++i) printf(" %lld/%lld", (long long)(h[16 + i] - h[0]), (long long)(h[32 + i] - h[0]));
+      printf("\n");
+      const int order[9] = {48, 49, 50, 51, 57, 54, 55, 56, 52};
+      const char* dn[9] = {"block 16 start (reference known)", "first chunk in registers", "chunk 0: 32 ex2 done",
+                           "chunk 0: sums + packs done", "chunk 0: tcgen05.st issued", "chunk 1 in registers",
+                           "chunk 1: 32 ex2 done", "chunk 1 stored", "P(16) published"};
+      for (int i = 0; i < 9; ++i) printf("    warp 2  %-40s %8lld\n", dn[i], (long long)(h[order[i]] - h[48]));
+    }
     test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, true);
     return g_fail ? 1 : 0;
   }
