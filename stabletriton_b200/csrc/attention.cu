@@ -303,10 +303,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 // ------------------------------------------------------------------------------------------------
 // Pipelined variant for Tk > 128 (self-attention): ONE CTA per SM that owns all 512 TMEM columns, so S and P
-// are double-buffered and O accumulates in TMEM across the whole K/V sweep; 448 threads, warp-specialised:
+// are double-buffered and O accumulates in TMEM across the whole K/V sweep; 480 threads, warp-specialised:
 //
 //   warp 0      TMA producer: Q once, K and V rings (4 stages each)
-//   warp 1      MMA issuer:   S(0); for j: S(j+1) -> wait P(j) -> O += P(j) V(j)     (S(j+1) runs under softmax(j))
+//   warp 14     S issuer:     S(0), S(1); for j: wait s_free(j) -> S(j+2)          (S runs two blocks ahead)
+//   warp 1      P.V issuer:   for j: wait P(j) -> O += P(j) V(j)
 //   warps 2-9   exp warps:    two per TMEM lane quadrant, each owning half of every row: stream S(j) out of TMEM
 //               in 16-column chunks (next chunk in flight while this one is processed), p = 2^(s*c - m),
 //               packed bf16 P(j) -> TMEM, partial row sums.  Nothing but the MUFU-bound stream.
@@ -322,7 +323,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // the two-CTA kernel above spends ~2.7 k cycles per block and SM because each CTA's MMA -> max -> exp -> MMA
 // chain is serial (single S / P buffers in 256 columns) and both CTAs hit the MUFU phase together.
 constexpr int kA3Stages = 4;
-constexpr int kA3Threads = 448;
+constexpr int kA3Threads = 480;
 constexpr int kA3SmemBytes = kAttnTileBytes * (1 + 2 * kA3Stages) + 256 + 2048 + 1024;
 constexpr int kA3TmemCols = 512;
 constexpr float kA3Tau = 8.f;  // log2 units
@@ -347,7 +348,8 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   uint64_t* p_full = m_ready + 2;          // [3]
   uint64_t* pv_done = p_full + 3;          // [2]
   uint64_t* s_free = pv_done + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* p_free = s_free + 2;           // [3]  P(i).V(i) has drained P buffer i % 3
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 3);
   float* s_m = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 buffers][128 rows] references
   float* s_l = s_m + 256;                                                         // [2 halves][128 rows] row sums
 
@@ -376,7 +378,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       mbar_init(&pv_done[i], 1);
       mbar_init(&s_free[i], 256);
     }
-    for (int i = 0; i < 3; ++i) mbar_init(&p_full[i], 256);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&p_full[i], 256);
+      mbar_init(&p_free[i], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<kA3TmemCols>(tmem_slot);
@@ -409,15 +414,17 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         tma_load_4d(sV + st * kAttnTileBytes, &tmap_v, &v_full[st], 0, j * kAttnBlockKV, h, b);
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kAttnBlockKV, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);        // P (TMEM)    x V (MN-major)
+  } else if (warp == 1 || warp == 14) {
+    // ===================================== MMA issuers ======================================
+    // Two issuing warps on different SM sub-partitions: warp 14 the S = Q K^T products (4 MMAs per block), warp 1 the
+    // O += P V products (8 per block).  A single issuer (~250 instructions per block, all on one scheduler) made the
+    // two exp warps that share its sub-partition the slowest of the eight, and the slowest quadrant sets the pace.
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, kAttnBlockKV, 0, 0);  // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);        // P (TMEM)    x V (MN-major)
+    constexpr uint32_t kTileStep = kAttnTileBytes >> 4;
+    if (warp == 14) {
       const uint64_t desc_q = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
       const uint64_t desc_k0 = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
-      const uint64_t desc_v0 = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
-      constexpr uint32_t kTileStep = kAttnTileBytes >> 4;
       auto issue_s = [&](int j) {
         const int st = j % kA3Stages;
         mbar_wait(&k_full[st], (j / kA3Stages) & 1);
@@ -432,16 +439,18 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       mbar_wait(q_full, 0);
       issue_s(0);
       if (nkv > 1) issue_s(1);
+      // S(j+2) goes out as soon as the exp warps have pulled S(j) out of TMEM (s_free, a quarter into block j); the
+      // max warps read S(j) before that (the exp warps wait for m_ready(j)).  So the S -> max -> reference chain of
+      // block j+2 starts well over a block ahead of its use.
+      for (int j = 0; j + 2 < nkv; ++j) {
+        mbar_wait(&s_free[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        issue_s(j + 2);
+      }
+    } else {
+      const uint64_t desc_v0 = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kA3Stages;
-        // S(j+2) goes out as soon as the exp warps have pulled the last of S(j) out of TMEM (s_free, ~300 cycles
-        // before they publish P(j)); the max warps read S(j) before that (the exp warps wait for m_ready(j)).  So
-        // the S -> max -> reference chain of block j+2 starts more than a block ahead of its use.
-        if (j + 2 < nkv) {
-          mbar_wait(&s_free[j & 1], (j >> 1) & 1);
-          tc_fence_after();
-          issue_s(j + 2);
-        }
         mbar_wait(&p_full[j % 3], (j / 3) & 1);
         if (j == 2 && lane == 0) AT_TRACE(8);
         mbar_wait(&v_full[st], (j / kA3Stages) & 1);
@@ -452,11 +461,12 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)
           umma_bf16_ts_elect(tmem_O, a + kk * 8, dv + 128 * kk, idesc_o, (j > 0) || (kk != 0));
         umma_commit_elect(&v_empty[st]);
+        umma_commit_elect(&p_free[j % 3]);
         umma_commit_elect(&pv_done[j & 1]);
         if (j == 2 && lane == 0) AT_TRACE(9);
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp >= 10) {  // 10..13
     // ===================================== max warps ========================================
     float m = -INFINITY;  // reference of my row (scaled scores, log2 domain)
     for (int j = 0; j < nkv; ++j) {
@@ -509,6 +519,11 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       }
       m = m_new;
       s_m[buf * 128 + row] = m;
+      // P is triple-buffered and P(j) overwrites P(j-3): publishing m(j) also vouches that P(j-3).V(j-3) has drained
+      // (this warp runs a block ahead and has the time to look; the exp warps do not)
+      // (its own barrier per buffer: the next arrival on p_free[j % 3] is P(j).V(j), which needs this very m(j), so
+      // the parity wait cannot alias)
+      if (j >= 3) mbar_wait(&p_free[j % 3], (j / 3 - 1) & 1);
       tc_fence_before();
       if (j == 2 && warp == 10 && lane == 0) AT_TRACE(12);
       if ((j == 16 || j == 17) && lane == 0) AT_TRACE(16 * (j - 15) + 8 + warp - 10);
@@ -543,8 +558,8 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       if (j == nkv - 1 && warp == 2 && lane == 0) AT_TRACE(10);
       if ((j == 16 || j == 17) && lane == 0) AT_TRACE(16 * (j - 15) + warp - 2);  // per-warp block period / skew
       const uint32_t t_s = tmem_S + buf * 128 + lane_off + half * 64;
-      // P is triple-buffered: P(j) overwrites P(j-3), and P(j-3).V(j-3) was issued before S(j), whose commit the
-      // max warps saw before publishing m(j) -- so knowing m(j) proves the buffer is free, no barrier to poll
+      // P is triple-buffered: P(j) overwrites P(j-3), and the max warps only publish m(j) once P(j-3).V(j-3) has
+      // drained -- so knowing m(j) proves the buffer is free, no barrier to poll here
       const uint32_t t_p = tmem_P + (j % 3) * 64 + lane_off + half * 32;
       float m;
       if (!pre) {
