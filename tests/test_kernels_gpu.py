@@ -141,6 +141,30 @@ def test_attention(K, b, h, tq, tk):
         assert torch.equal(got2, got)
 
 
+@pytest.mark.parametrize("tk,growth", [(1024, 24.0), (1000, -0.9), (300, 6.0), (129, 6.0)])
+def test_attention_reference_moves(K, tk, growth):
+    """Self-attention sweep kernel (Tk > 128): keys scaled by 1 + growth * t / Tk make later K/V blocks carry much larger
+    (or much smaller) scores, which exercises the lazy softmax-reference update -- O rescaled in tensor memory when the
+    running row maximum grows by more than 2^8 -- the ragged last block and the single-key last block."""
+    b, h, tq = 1, 2, 256
+    q, k, v = rnd(b, tq, h * 64, seed=41) * 1.5, rnd(b, tk, h * 64, seed=42) * 1.5, rnd(b, tk, h * 64, seed=43)
+    ramp = (1.0 + growth * torch.arange(tk, dtype=torch.float32) / tk).view(1, tk, 1)
+    k = (k.float() * ramp).to(torch.bfloat16)
+    ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
+    got = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+    check(got.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
+
+
+def test_attention_long_sweep(K):
+    """T = 16384 (the 2048^2 self-attention of SURVEY 8d config 5) against fp32 softmax(QK^T)V on the GPU, one head."""
+    b, h, t = 1, 1, 16384
+    q, k, v = (rnd(b, t, h * 64, seed=s).cuda() for s in (44, 45, 46))
+    got = K.attention_btc(q, k, v, h, 0.125)
+    qf, kf, vf = (x.float().view(b, t, h, 64).transpose(1, 2) for x in (q, k, v))
+    ref = torch.softmax(qf[:, :, :2048] @ kf.transpose(-2, -1) * 0.125, dim=-1) @ vf  # first 2048 query rows, fp32
+    check(got.view(b, t, h, 64).transpose(1, 2)[:, :, :2048].float().cpu(), ref.cpu(), rel_tol=2e-2, cos_tol=0.9995)
+
+
 @pytest.mark.parametrize("n,c,k,hw,mode", [
     (2, 320, 320, 128, "temb"), (2, 640, 640, 64, "res"), (2, 1280, 1280, 32, "temb"), (2, 960, 640, 64, "plain"),
     (2, 2560, 1280, 32, "plain"), (1, 64, 128, 16, "res"), (3, 64, 64, 8, "temb"),  # small maps: multi-image tiles
