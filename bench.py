@@ -59,12 +59,33 @@ def load_oracle():
     return mod
 
 
+def physical_cores() -> int:
+    """Distinct (package, core) pairs from /proc/cpuinfo -- what torch's default intra-op pool uses; SMT siblings slow
+    the fp32 GEMMs down."""
+    try:
+        pairs, phys = set(), None
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("physical id"):
+                    phys = ln.split(":")[1].strip()
+                elif ln.startswith("core id"):
+                    pairs.add((phys, ln.split(":")[1].strip()))
+        if pairs:
+            return len(pairs)
+    except OSError:
+        pass
+    return os.cpu_count() or 1
+
+
 def cpu_reference_times(timed: int, warmup: int):
     """Seconds per fp32 UNet forward of the oracle port at config 1 (B=1, 4x64x64), all host threads."""
     import torch
     from stabletriton_b200 import UNet2DConditionModel, UNetConfig, synth
 
-    cores = torch.get_num_threads()  # torch's default intra-op pool = all host cores
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+        # torchrun pins every rank to one OpenMP thread; the CPU arm runs on rank 0 alone and may use the whole host
+        torch.set_num_threads(physical_cores())
+    cores = torch.get_num_threads()  # torch's default intra-op pool = all physical host cores
     oracle = load_oracle()
     cfg = UNetConfig.sdxl()
     with torch.device("meta"):
@@ -110,7 +131,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -323,7 +344,7 @@ def run_gpu_arm(args):
         }
         # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the contract asks for it at N=1 only (torchrun also pins OMP to 1 thread)
             times, cores = cpu_reference_times(timed=2, warmup=1)
             sec = statistics.median(times)
             cpu = {
@@ -354,7 +375,7 @@ def run_gpu_arm(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -371,7 +392,27 @@ def ncu_gemm_traffic_per_launch():
         return None
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL prints its version banner to fd 1 when the first communicator is
+    created, so fd 1 is pointed at stderr for the whole run and the JSON line is written to a duplicate of the original."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
