@@ -42,7 +42,6 @@ struct AttnParams {
   int H, Tq, Tk;
   float scale_log2;
   unsigned long long* trace;  // debug: 16 clock64 stamps for CTA (0,0), or nullptr
-  int skew;                   // pipelined kernel: start-up delay (cycles) of the second exp warp of each quadrant
 };
 
 // Registers are allocated per group of 4 warps: the 10 warps of this CTA cost as much as 12, so two resident
@@ -535,16 +534,6 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     const int half = (warp - 2) >> 2;
     const uint32_t pair_bar = 1 + quad;
     float m_prev = -INFINITY, l = 0.f;  // l: my half of the row sum, relative to m_prev
-    // The two warps of a quadrant share an SM sub-partition (scheduler + MUFU).  Started together they stay in
-    // lock step -- both in the barrier / TMEM-latency part of a block, then both fighting for the MUFU.  Half a
-    // block of skew lets one warp's ex2 stream cover the other's latencies (S and P are double-buffered, so a
-    // warp may run up to a block ahead).
-    if (half == 1 && p.skew > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.skew) {
-      }
-    }
-
     // S(j) arrives in two 32-column chunks per thread (va, vb).  While the second chunk of block j is being
     // exponentiated, the first chunk of block j+1 is already requested (its reference is normally published a
     // block ahead), so the barrier / shared-memory / TMEM latencies at a block boundary hide under the MUFU stream.
@@ -776,11 +765,6 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   p.Tk = Tk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
-  static const int skew = [] {
-    const char* e = getenv("ST_ATTN_SKEW");
-    return e ? atoi(e) : 0;
-  }();
-  p.skew = skew;
   const dim3 grid((Tq + kAttnBlockQ - 1) / kAttnBlockQ, B * H);
   // one K/V block (cross-attention, Tk = 77): the two-CTA-per-SM kernel; longer sweeps: the pipelined one
   static const int force = [] {

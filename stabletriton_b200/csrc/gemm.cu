@@ -69,27 +69,6 @@ static int choose_block_n(int M, int n_cols, bool geglu, int K) {
   return best;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-static int gemm_l2_prefetch() {
-  static const int v = env_int("ST_GEMM_L2PF", 0);
-  return v;
-}
-static int gemm_l2_prefetch_mod() {
-  static const int v = env_int("ST_GEMM_L2PF_MOD", 1);
-  return v > 0 ? v : 1;
-}
-
-static int gemm_ramp() {
-  static const int v = [] {
-    const char* e = getenv("ST_GEMM_RAMP");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
-}
-
 template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false, bool kCluster = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
                        cudaStream_t stream) {
@@ -241,9 +220,6 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.trace = g_gemm_trace;
   p.stream_k = stream_k ? 1 : 0;
   p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
-  p.ramp = gemm_ramp();
-  p.l2_prefetch = (flags & ST_W_STATIC) ? gemm_l2_prefetch() : 0;
-  p.l2_prefetch_mod = gemm_l2_prefetch_mod();
   p.ws = sk_ws;
   p.flags = sk_flags;
   p.cluster = (!stream_k && want_cluster(M, n_out, block_n, geglu)) ? 1 : 0;
@@ -319,9 +295,6 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.trace = g_gemm_trace;
   p.stream_k = stream_k ? 1 : 0;
   p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
-  p.ramp = gemm_ramp();
-  p.l2_prefetch = (flags & ST_W_STATIC) ? gemm_l2_prefetch() : 0;
-  p.l2_prefetch_mod = gemm_l2_prefetch_mod();
   p.ws = sk_ws;
   p.flags = sk_flags;
   p.cluster = (!stream_k && want_cluster(N * H * W, K, block_n, false)) ? 1 : 0;

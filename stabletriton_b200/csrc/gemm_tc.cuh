@@ -52,10 +52,8 @@ struct GemmParams {
   // contiguous ranges; a CTA that starts in the middle of a tile dumps its fp32 partial into
   // ws[blockIdx.x] and raises flags[blockIdx.x]; the CTA that owns the head of the tile merges them.
   int stream_k;
-  int ramp;      // debug/tuning: number of k-blocks requested before waiting for the first to land (0 = off)
   int w_static;  // W is not written by the preceding kernel: prefetch it ahead of the PDL wait
   int cluster;   // host-side choice: launch the CTA-pair instantiation
-  int l2_prefetch, l2_prefetch_mod;  // weight-tile L2 prefetch distance (k-blocks, 0 = off) and issuing m-block stride
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
   // 4-D (conv) A addressing
@@ -226,7 +224,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int cursor = cursor0, tile, kb0, kb1;
         if (next_segment(cursor, tile, kb0, kb1)) {
           const int n_blk = tile / p.num_m_blocks;
-          prefetched = min((!kCluster && p.ramp > 0) ? min(p.ramp, STAGES) : STAGES, kb1 - kb0);
+          prefetched = min(STAGES, kb1 - kb0);
           for (int i = 0; i < prefetched; ++i) {
             uint8_t* sb = smem_ab + i * S::kStageBytes + S::kABytes;
             const int kb = kb0 + i;
@@ -238,7 +236,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
-      int ramp_left = kCluster ? 0 : p.ramp;  // (the peer of a pair never sees its own full barriers complete)
       const int cblocks = kConvA ? p.conv_C / kGemmBlockK : 1;
       int cursor = cursor0, tile, kb0, kb1;
       while (next_segment(cursor, tile, kb0, kb1)) {
@@ -277,28 +274,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0);
           }
           if (!b_in_flight) load_b(sb, &full_bar[stage], kb, n_blk);
-          // Weights are read once per step, so every B tile of the main loop is an HBM miss for the CTAs that
-          // share it (they run in lock step); the 4-stage ring only covers an L2-hit latency.  Ask L2 for the
-          // tile p.l2_prefetch k-blocks ahead (one CTA in p.l2_prefetch_mod per n-block does the asking).
-          if (p.l2_prefetch > 0 && (m_blk % p.l2_prefetch_mod) == 0 && kb + p.l2_prefetch < kb1) {
-            const int kp = (kb + p.l2_prefetch) * kGemmBlockK;
-            if (kGeglu) {
-              tma_prefetch_l2_2d(&tmap_b, kp, n_blk * (BLOCK_N / 2));
-              tma_prefetch_l2_2d(&tmap_b, kp, p.n_out + n_blk * (BLOCK_N / 2));
-            } else if (kCluster) {
-              tma_prefetch_l2_2d(&tmap_b, kp, n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2));
-            } else {
-              tma_prefetch_l2_2d(&tmap_b, kp, n_blk * BLOCK_N);
-            }
-          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
-          // Start-up ramp: requesting the whole ring at once makes stage 0 share the L2->SM fill with
-          // stages 1..STAGES-1 of every CTA, so the first MMA starts only when most of the ring has landed.
-          // Let the first p.ramp stages land before asking for the rest.
-          if (ramp_left > 0 && --ramp_left == 0) mbar_wait(&full_bar[0], 0);
         }
       }
     }

@@ -231,11 +231,6 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
       : "memory");
 }
 
-// L2 prefetch of a 2-D tile (no shared-memory destination, no completion to wait for)
-__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
-}
-
 // ---- thread-block clusters -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
