@@ -227,7 +227,10 @@ def run_gpu_arm(args):
     compiled = st.compile(model, cuda_graph=True)
 
     # ---- resident-input arm: step graph (UNet + scheduler) ---------------------------------------
-    loop = DenoiseLoop(compiled, prompts=prompts, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device)
+    # The headline step runs the WHOLE UNet every step, as the reference does (the prompt-constant K/V projections and
+    # text embedding are recomputed inside the timed region); the hoisted variant is reported separately below.
+    loop = DenoiseLoop(compiled, prompts=prompts, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device,
+                       hoist_prompt_constants=False)
     inp = synth.synth_inputs(prompts, latent, cfg, seed=1234 + rank, device=device, dtype=torch.bfloat16)
     cond = {"encoder_hidden_states": inp["encoder_hidden_states"], **inp["added_cond_kwargs"]}
     unc = synth.synth_inputs(prompts, latent, cfg, seed=4321 + rank, device=device, dtype=torch.bfloat16)
@@ -258,6 +261,24 @@ def run_gpu_arm(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+
+    # ---- informational: same loop with the prompt-constant part computed once per prompt ------------------
+    loop_h = DenoiseLoop(compiled, prompts=prompts, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device)
+    loop_h.set_conditioning(cond, uncond)
+    loop_h.reset(inp["sample"].float())
+    loop_h.capture()
+    loop_h.reset(inp["sample"].float())
+    for _ in range(warmup):
+        loop_h.run_step()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    h0.record()
+    for _ in range(steps):
+        loop_h.run_step()
+    h1.record()
+    barrier()
+    ms_hoisted = h0.elapsed_time(h1)
+    del loop_h
 
     # ---- e2e arm: public API, pinned-host inputs, H2D + D2H inside the timed region ----------------
     b2 = synth.synth_inputs(2 * prompts, latent, cfg, seed=99 + rank, device="cpu", dtype=torch.bfloat16)
@@ -294,9 +315,9 @@ def run_gpu_arm(args):
 
     # ---- max over ranks -------------------------------------------------------------------------------
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=device)
+        t = torch.tensor([ms_total, ms_e2e, ms_hoisted], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = t.tolist()
+        ms_total, ms_e2e, ms_hoisted = t.tolist()
 
     if rank == 0:
         peaks = load_peaks()
@@ -374,6 +395,10 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "prompt_constants_hoisted": {
+                "ms_per_step": ms_hoisted / steps, "value": world * prompts * steps / (ms_hoisted * 1e-3), "unit": UNIT,
+                "note": "not the headline: cross-attention K/V projections + text/time-ids embedding computed once per "
+                        "prompt (compiled.prepare / step_forward, SURVEY 8f rank 2) instead of inside every step"},
         }
         emit(line)
     if world > 1:

@@ -14,6 +14,7 @@ variants (+GEGLU, +residual, +activation) before the plain ones.
 """
 from __future__ import annotations
 
+import inspect
 import operator
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -571,6 +572,88 @@ def keep_channels_last(gm: fx.GraphModule) -> int:
                 n += 1
     _finish(gm)
     return n
+
+
+def split_prompt_constants(gm: fx.GraphModule, dynamic_inputs=("sample", "timesteps")):
+    """Split the rewritten graph into a prompt-constant prologue and the per-step body.
+
+    Everything that depends only on `encoder_hidden_states` / `added_cond_kwargs` -- the batched cross-attention K/V
+    projection (one 154 x 166400 x 2048 GEMM for SDXL) and the text/time-ids embedding MLP -- is the same for all steps
+    of a prompt (reference: unet_pt.py:123-132, 478-486 recompute it every step).  Returns
+
+        prologue : GraphModule(encoder_hidden_states, added_cond_kwargs) -> tuple of boundary tensors
+        body     : GraphModule(sample, timesteps, *boundary) -> [eps]
+        n        : number of boundary tensors
+
+    Both share parameters / buffers / submodules with `gm`; `gm` itself is left untouched, so the plain forward keeps
+    the reference's four-argument signature.
+    """
+    g = gm.graph
+    nodes = list(g.nodes)
+    placeholders = [n for n in nodes if n.op == "placeholder"]
+    dyn_roots = {n for n in placeholders if n.target in dynamic_inputs}
+    static_roots = [n for n in placeholders if n not in dyn_roots]
+    dynamic, prompt_dep = set(dyn_roots), set(static_roots)
+    # `x.to(emb.dtype)` (unet_pt.py:486) makes the text/time-ids embedding depend on a step tensor through its dtype
+    # only.  Every activation of the engine has the parameter dtype (compile() checks it), so such a dtype is a
+    # constant of the model, not of the step.
+    param_dtype = next(gm.parameters()).dtype
+    dtype_consts = set()
+    for n in nodes:  # topological order
+        if n.op in ("placeholder", "output"):
+            continue
+        if n.op == "call_function" and n.target is getattr and len(n.args) == 2 and n.args[1] == "dtype":
+            dtype_consts.add(n)
+            continue
+        ins = [a for a in n.all_input_nodes if a not in dtype_consts]
+        if any(a in dynamic for a in ins):
+            dynamic.add(n)
+        elif any(a in prompt_dep for a in ins):
+            prompt_dep.add(n)  # depends on the prompt only
+        # else: "free" (get_attr and pure functions of constants) -- copied wherever it is needed
+    output = next(n for n in nodes if n.op == "output")
+    boundary = [n for n in nodes if n in prompt_dep and n.op != "placeholder"
+                and any((u in dynamic) or (u is output) for u in n.users)]
+
+    def build(is_body: bool):
+        new = fx.Graph()
+        env: Dict[Node, Node] = {}
+        if is_body:
+            for ph in placeholders:
+                if ph in dyn_roots or any(u in dynamic for u in ph.users):
+                    env[ph] = new.placeholder(ph.target, default_value=ph.args[0] if ph.args else inspect.Signature.empty)
+            for i, b in enumerate(boundary):
+                env[b] = new.placeholder(f"prompt_const_{i}")
+        else:
+            for ph in static_roots:
+                env[ph] = new.placeholder(ph.target)
+
+        def copy(n):
+            if n in dtype_consts:
+                return param_dtype
+            if n in env:
+                return env[n]
+            assert n.op != "placeholder", f"{n.target} is not an input of this half"
+            if is_body:
+                assert n not in prompt_dep, f"prompt-constant node {n.name} leaked into the step body"
+            else:
+                assert n not in dynamic, f"step-dependent node {n.name} leaked into the prologue"
+            for a in n.all_input_nodes:
+                copy(a)
+            env[n] = new.node_copy(n, lambda x: param_dtype if x in dtype_consts else env[x])
+            return env[n]
+
+        if is_body:
+            for n in nodes:
+                if n in dynamic and n.op != "placeholder" and n not in dtype_consts:
+                    copy(n)
+            new.output(fx.node.map_arg(output.args[0], lambda x: copy(x)))
+        else:
+            new.output(tuple(copy(b) for b in boundary))
+        new.lint()
+        return fx.GraphModule(gm, new, type(gm).__name__ + ("Step" if is_body else "PromptConstants"))
+
+    return build(False), build(True), len(boundary)
 
 
 def census(gm: fx.GraphModule) -> Dict[str, int]:

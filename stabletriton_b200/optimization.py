@@ -15,7 +15,11 @@ Differences, all deliberate:
   * every Linear and Conv2d is swapped too (the reference disabled its Linear pass and never had a
     working conv, SURVEY F7), with bias / SiLU / GEGLU / time-embedding / residual epilogues fused;
   * `.config` is carried over, so `pipe.unet = compile(unet)` needs no manual patch
-    (cf. implementations/Diffusers/load_sdxl_pipeline.py:29-34).
+    (cf. implementations/Diffusers/load_sdxl_pipeline.py:29-34);
+  * besides forward(), the returned module offers `prepare(encoder_hidden_states, added_cond_kwargs)` and
+    `step_forward(sample, timesteps, *prompt_constants)`: the prompt-constant part of the graph (cross-attention K/V
+    projections, text / time-ids embedding) computed once per prompt instead of once per step (pipeline.DenoiseLoop
+    uses them).
 """
 from __future__ import annotations
 
@@ -107,6 +111,21 @@ def optimize_model(model: torch.nn.Module, cuda_graph: bool = True, *, check_dev
     if cfg is not None:
         gm.cfg = cfg
     gm.eval()
+    # Prompt-constant hoisting: `prepare` computes what depends on the prompt only (all cross-attention
+    # K/V projections, the text / time-ids embedding), `step_forward` is the rest.  forward() itself is unchanged.
+    prologue, body, n_consts = P.split_prompt_constants(gm)
+    prologue.eval()
+    body.eval()
+
+    def prepare(encoder_hidden_states, added_cond_kwargs):
+        with torch.no_grad():
+            return tuple(prologue(encoder_hidden_states, added_cond_kwargs))
+
+    def step_forward(sample, timesteps, *prompt_constants):
+        with torch.no_grad():
+            return body(sample, timesteps, *prompt_constants)
+
+    gm.prepare, gm.step_forward, gm.num_prompt_constants = prepare, step_forward, n_consts
     if cuda_graph:
         eager_forward = gm.forward
 

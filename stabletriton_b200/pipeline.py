@@ -60,8 +60,14 @@ class DenoiseLoop:
     """
 
     def __init__(self, unet, prompts: int, latent_hw: int, num_steps: int = 30, guidance: float = 5.0,
-                 in_channels: int = 4, device="cuda", cfg_row: Optional[int] = None, group=None):
+                 in_channels: int = 4, device="cuda", cfg_row: Optional[int] = None, group=None,
+                 hoist_prompt_constants: bool = True):
         self.unet_fn = getattr(unet, "eager_forward", unet)
+        # compile() also exposes the graph split at the prompt / step boundary: K/V projections of the text context and
+        # the text / time-ids embedding are computed in set_conditioning(), not in every step
+        self.prepare_fn = getattr(unet, "prepare", None) if hoist_prompt_constants else None
+        self.step_fn = getattr(unet, "step_forward", None) if self.prepare_fn is not None else None
+        self.consts = None
         self.P, self.hw, self.steps, self.guidance = prompts, latent_hw, num_steps, float(guidance)
         self.C = in_channels
         self.device = torch.device(device)
@@ -92,7 +98,10 @@ class DenoiseLoop:
         copies = 1 if self.cfg_row is not None else 2
         _cabi.check(L.st_scale_model_input(self.x.data_ptr(), self.model_in.data_ptr(), n, copies,
                                            self.sigmas.data_ptr(), self.step.data_ptr(), stream), "scale_model_input")
-        eps = self.unet_fn(self.model_in, self.t_cur, self.ctx, self.added)[0]
+        if self.step_fn is not None:
+            eps = self.step_fn(self.model_in, self.t_cur, *self.consts)[0]
+        else:
+            eps = self.unet_fn(self.model_in, self.t_cur, self.ctx, self.added)[0]
         if not eps.is_contiguous():
             eps = eps.contiguous()
         if self.cfg_row is None:
@@ -125,6 +134,14 @@ class DenoiseLoop:
             self.ctx.copy_(ctx)
             self.added["text_embeds"].copy_(text)
             self.added["time_ids"].copy_(ids)
+        if self.prepare_fn is not None:
+            with torch.no_grad():
+                fresh = self.prepare_fn(self.ctx, self.added)
+            if self.consts is None:
+                self.consts = list(fresh)  # these addresses are what the captured step graph reads
+            else:
+                for dst, src in zip(self.consts, fresh):
+                    dst.copy_(src)
 
     def reset(self, latents: torch.Tensor) -> None:
         """latents: (P, C, H, W) unit-variance noise.  x0 = latents * init_noise_sigma; step = 0."""

@@ -51,6 +51,27 @@ def test_tiny_rewrite_leaves_no_module_calls_and_preserves_output():
     assert isinstance(gm(**inp) if False else [out], list)
 
 
+def test_prompt_constant_split_is_exact():
+    """prepare() + step_forward() == forward(), bit for bit; the prologue holds exactly the prompt-only work."""
+    cfg, model, gm = _compiled_tiny()
+    pro, body, n = P.split_prompt_constants(gm)
+    assert n == gm.num_prompt_constants == 1 + 2 * 17  # embedding MLP hidden + K and V of 17 cross-attention layers
+    assert P.census(pro) == {"timestep_wrapper": 1, "linear_wrapper": 1, "linear_wrapper_functional": 1}
+    assert [x.target for x in pro.graph.nodes if x.op == "placeholder"][:2] == ["encoder_hidden_states", "added_cond_kwargs"]
+    body_inputs = [x.target for x in body.graph.nodes if x.op == "placeholder"]
+    assert body_inputs[:2] == ["sample", "timesteps"] and len(body_inputs) == 2 + n
+    inp = synth.synth_inputs(2, 16, cfg, seed=5)
+    with torch.no_grad(), fake_kernels.installed():
+        ref = gm(**inp)[0]
+        consts = gm.prepare(inp["encoder_hidden_states"], inp["added_cond_kwargs"])
+        out = gm.step_forward(inp["sample"], inp["timesteps"], *consts)[0]
+        # a different step with the same prompt reuses the constants
+        inp2 = dict(inp, sample=inp["sample"] * 0.5, timesteps=torch.tensor(17.0))
+        ref2 = gm(**inp2)[0]
+        out2 = gm.step_forward(inp2["sample"], inp2["timesteps"], *consts)[0]
+    assert torch.equal(out, ref) and torch.equal(out2, ref2)
+
+
 def test_pass_counts_on_sdxl_architecture():
     with torch.device("meta"):
         model = UNet2DConditionModel(UNetConfig.sdxl())
