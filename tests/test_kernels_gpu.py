@@ -228,3 +228,19 @@ def test_shape_and_dtype_errors_are_raised_before_launch(K):
         K.attention_btc(rnd(1, 8, 100).cuda(), rnd(1, 8, 100).cuda(), rnd(1, 8, 100).cuda(), 2, 0.1)
     with pytest.raises(ValueError):
         K.conv2d(rnd(1, 64, 12, 12).cuda(), rnd(64, 64, 3, 3).cuda(), None)  # 144 pixels: not tileable
+
+
+def test_2048px_shapes(K):
+    """SURVEY 8d config 5 (256 x 256 latents): the largest activations of the path, against fp32 torch on the GPU."""
+    x = rnd(2, 320, 256, 256, seed=51).cuda().contiguous(memory_format=torch.channels_last)
+    w, b = rnd(320, 320, 3, 3, scale=2880 ** -0.5, seed=52).cuda(), (rnd(320, seed=53) * 0.1).cuda()
+    ref = F.conv2d(x.float(), w.float(), b.float(), padding=1)
+    check(K.conv2d(x, w, b).float().cpu(), ref.cpu())
+    gw, gb = (1 + 0.1 * rnd(320, seed=54)).cuda(), (0.1 * rnd(320, seed=55)).cuda()
+    ref = F.silu(F.group_norm(x.float(), 32, gw.float(), gb.float(), 1e-5))
+    check(K.groupnorm_wrapper(x, 32, gw, gb, 1e-5, activation=True).float().cpu(), ref.cpu())
+    t = rnd(32768, 640, seed=56).cuda()
+    lw, lb = (1 + 0.1 * rnd(640, seed=57)).cuda(), (0.1 * rnd(640, seed=58)).cuda()
+    check(K.layer_norm(t, lw, lb, 1e-5).float().cpu(), F.layer_norm(t.float(), (640,), lw.float(), lb.float(), 1e-5).cpu())
+    wl, bl = rnd(1920, 640, scale=640 ** -0.5, seed=59).cuda(), (rnd(1920, seed=60) * 0.1).cuda()
+    check(K.linear(t, wl, bl).float().cpu(), F.linear(t.float(), wl.float(), bl.float()).cpu())

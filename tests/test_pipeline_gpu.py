@@ -83,3 +83,25 @@ def test_schedule_tables_on_device(built_lib):
     t, s, init = euler_schedule(30)
     assert torch.equal(loop.timesteps[:30].cpu(), t) and torch.equal(loop.sigmas.cpu(), s)
     assert abs(loop.init_noise_sigma - init) < 1e-9 and loop.timesteps.numel() == 31
+
+
+def test_hoisted_and_unhoisted_loops_agree(built_lib):
+    """The loop with the prompt-constant prologue (default) and the loop that recomputes it every step give the same
+    latents bit for bit, and new conditioning refreshes the constants in place (captured graph keeps working)."""
+    import stabletriton_b200 as st
+    from stabletriton_b200 import UNetConfig, synth
+    from stabletriton_b200.pipeline import DenoiseLoop
+
+    cfg = UNetConfig.tiny()
+    compiled = st.compile(synth.build_unet(cfg, seed=3), cuda_graph=True)
+    noise = synth.synth_tensor("latents", (1, cfg.in_channels, 32, 32), 77) * (3.0 ** 0.5)
+    c1, u1 = _conditioning(cfg, 1, 1, "cuda", torch.bfloat16), _conditioning(cfg, 1, 2, "cuda", torch.bfloat16)
+    c2, u2 = _conditioning(cfg, 1, 3, "cuda", torch.bfloat16), _conditioning(cfg, 1, 4, "cuda", torch.bfloat16)
+    hoisted = DenoiseLoop(compiled, prompts=1, latent_hw=32, num_steps=6)
+    plain = DenoiseLoop(compiled, prompts=1, latent_hw=32, num_steps=6, hoist_prompt_constants=False)
+    assert hoisted.step_fn is not None and plain.step_fn is None
+    for cond, uncond in ((c1, u1), (c2, u2)):  # the second pass reuses the captured graphs with new prompts
+        a = hoisted.run(noise, cond, uncond, use_graph=True)
+        b = plain.run(noise, cond, uncond, use_graph=True)
+        assert torch.equal(a, b)
+    assert not torch.equal(hoisted.run(noise, c1, u1), a)  # (different prompts do give different latents)

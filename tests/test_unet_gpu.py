@@ -41,7 +41,7 @@ def _build(cfg, seed, device="cuda"):
     return synth.build_unet(cfg, seed=seed, device=device, dtype=torch.bfloat16)
 
 
-@pytest.mark.parametrize("batch,latent", [(2, 32), (1, 16)])
+@pytest.mark.parametrize("batch,latent", [(2, 32), (1, 16), (16, 16)])  # 16 = 8 prompts x CFG
 def test_tiny_unet_matches_oracle(built_lib, batch, latent):
     import stabletriton_b200 as st
     from stabletriton_b200 import UNetConfig, synth, _cabi
@@ -113,3 +113,39 @@ def test_sdxl_unet_matches_reference_golden(built_lib, golden_dir):
     print(f"SDXL B=1 64x64 vs reference fp32: rel={rel:.3e} cos={cos:.6f} launches(capture+warmup)={_cabi.launch_count()}")
     print("pass report:", compiled.pass_report)
     assert rel <= REL_TOL and cos >= COS_TOL, (rel, cos)
+
+
+def test_prepare_plus_step_forward_equals_forward(built_lib):
+    """Prompt-constant hoisting on the GPU: prepare() + step_forward() is bit-identical to forward()."""
+    import stabletriton_b200 as st
+    from stabletriton_b200 import UNetConfig, synth
+
+    cfg = UNetConfig.tiny()
+    compiled = st.compile(_build(cfg, seed=3), cuda_graph=False)
+    inp = _to_dev(synth.synth_inputs(2, 32, cfg, seed=11), "cuda", torch.bfloat16)
+    with torch.no_grad():
+        ref = compiled(**inp)[0]
+        consts = compiled.prepare(inp["encoder_hidden_states"], inp["added_cond_kwargs"])
+        assert len(consts) == compiled.num_prompt_constants == 35
+        out = compiled.step_forward(inp["sample"], inp["timesteps"], *consts)[0]
+        again = compiled.step_forward(inp["sample"] * 0.5, torch.tensor(17.0, device="cuda"), *consts)[0]
+        ref2 = compiled(inp["sample"] * 0.5, torch.tensor(17.0, device="cuda"), inp["encoder_hidden_states"],
+                        inp["added_cond_kwargs"])[0]
+    assert torch.equal(out, ref) and torch.equal(again, ref2)
+
+
+def test_checkpoint_round_trip_through_the_engine(built_lib, tmp_path):
+    """Diffusers-layout safetensors -> load_diffusers_unet -> compile(): same output as the model that wrote the file."""
+    import stabletriton_b200 as st
+    from stabletriton_b200 import UNetConfig, synth
+
+    cfg = UNetConfig.tiny()
+    model = _build(cfg, seed=9)
+    st.save_diffusers_unet(model, os.path.join(tmp_path, "unet"), cfg)
+    loaded = st.load_diffusers_unet(os.path.join(tmp_path, "unet"))
+    assert next(loaded.parameters()).dtype == torch.bfloat16 and next(loaded.parameters()).is_cuda
+    inp = _to_dev(synth.synth_inputs(2, 16, cfg, seed=5), "cuda", torch.bfloat16)
+    with torch.no_grad():
+        a = st.compile(model, cuda_graph=False)(**inp)[0]
+        b = st.compile(loaded, cuda_graph=False)(**inp)[0]
+    assert torch.equal(a, b)
