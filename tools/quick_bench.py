@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--latent", type=int, default=128)
     ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--leave-one-out", action="store_true",
+                    help="in-sequence marginal cost of each kernel family: time the whole launch sequence with that "
+                         "family's launches left out (outputs are garbage, timing is not)")
     args = ap.parse_args()
     cfg = UNetConfig.tiny() if args.tiny else UNetConfig.sdxl()
     t0 = time.time()
@@ -86,6 +89,44 @@ def main():
         elif name == "st_layernorm_bf16":
             key += f" M{a[6]} N{a[7]}"
         fam.setdefault(key, []).append((name, a))
+    if args.leave_one_out:
+        def group(name, a):
+            if name == "st_gemm_bf16":
+                m, n, k = a[6], a[7], a[8]
+                if m == 2048 and n == 1280 and k == 1280:
+                    return "gemm 2048x1280x1280"
+                if m == 2048 and k == 5120:
+                    return "gemm 2048x1280x5120 (ff out)"
+                if m == 2048 and n == 3840:
+                    return "gemm 2048x3840x1280 (qkv)"
+                if m == 2048 and n == 10240:
+                    return "gemm 2048x10240x1280 (geglu)"
+                if m == 8192:
+                    return "gemm M=8192 (64x64 level)"
+                return "gemm other"
+            if name == "st_conv3x3_nhwc_bf16":
+                return "conv3x3"
+            if name == "st_attention_bf16":
+                return f"attention Tq{a[18]} Tk{a[19]}"
+            if name == "st_groupnorm_nhwc_bf16":
+                return "groupnorm"
+            if name == "st_layernorm_bf16":
+                return "layernorm"
+            return "glue"
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            full = time_graph(lambda: _cabi.replay(calls, torch.cuda.current_stream().cuda_stream), iters=10)
+        print(f"  all {len(calls)} launches replayed in sequence: {full:.3f} ms")
+        groups = sorted({group(n, a) for n, a in calls})
+        for gname in groups:
+            rest = [(n, a) for n, a in calls if group(n, a) != gname]
+            only = [(n, a) for n, a in calls if group(n, a) == gname]
+            with torch.cuda.stream(stream):
+                t_rest = time_graph(lambda: _cabi.replay(rest, torch.cuda.current_stream().cuda_stream), iters=10)
+                t_only = time_graph(lambda: _cabi.replay(only, torch.cuda.current_stream().cuda_stream), iters=10)
+            print(f"  {gname:40s} launches={len(only):4d}  in sequence {full - t_rest:7.3f} ms   alone {t_only:7.3f} ms")
+        return
+
     stream = torch.cuda.Stream()
     total = 0.0
     for name, lst in sorted(fam.items()):
