@@ -359,6 +359,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int row = m_blk * kGemmBlockM + tile_row;
       const int n0 = n_blk * kOutCols;
       const bool row_ok = row < p.M;
+      // Last tile of this CTA (for the single-wave GEMMs: the only one): no operand load is in flight or will be
+      // issued any more and every MMA has retired once the accumulator barrier fires, so the smem ring is free --
+      // each 64-column group gets its own 16 KB staging tile there instead of sharing one.  That removes, per
+      // group, the wait for the previous bulk store to finish reading the tile and one of the two 256-thread
+      // barriers, on the only epilogue that is not hidden behind a following main loop.
+      const bool ring_staging = !kStreamK && !kCluster && cursor >= num_tiles && kGroups * S::kOutStageBytes <= STAGES * S::kStageBytes;
       float* sb = s_bias + acc * BLOCK_N;
       const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
 
@@ -476,8 +482,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(7);
         // the staging tile is reused per group: wait until the previous TMA store has read it
-        if (etid == 0) tma_store_wait_read();
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        uint8_t* s_stage = ring_staging ? smem_ab + g * S::kOutStageBytes : s_out;
+        if (!ring_staging) {
+          if (etid == 0) tma_store_wait_read();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(8);
         // All shared-memory reads of this chunk first (the compiler cannot hoist them over the staging
         // stores below: both live in shared memory), then straight-line register math on 32 columns.
@@ -537,14 +546,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           o.z = pack_bf16x2(x[j + 4], x[j + 5]);
           o.w = pack_bf16x2(x[j + 6], x[j + 7]);
           const int chunk = half * 4 + (j >> 3);
-          *reinterpret_cast<uint4*>(s_out + tile_row * 128 + ((chunk ^ (tile_row & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(s_stage + tile_row * 128 + ((chunk ^ (tile_row & 7)) << 4)) = o;
         }
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(9);
         // 64 columns staged: hand them to the TMA store engine (clips rows >= M and columns >= n_out)
         fence_proxy_async_smem();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (etid == 0) {
-          tma_store_2d(&tmap_d, s_out, n0 + g * 64, m_blk * kGemmBlockM);
+          tma_store_2d(&tmap_d, s_stage, n0 + g * 64, m_blk * kGemmBlockM);
           tma_store_commit();
         }
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(11);

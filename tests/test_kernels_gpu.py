@@ -48,6 +48,9 @@ def K(built_lib):
     (2, 320, 128, 32, True, 1e-5), (2, 640, 64, 32, True, 1e-5), (2, 1280, 32, 32, False, 1e-6),
     (2, 960, 64, 32, True, 1e-5), (2, 2560, 32, 32, True, 1e-5), (1, 1920, 32, 32, True, 1e-5),
     (3, 64, 10, 8, False, 1e-5),  # odd spatial size, non-SDXL group width
+    (2, 640, 128, 32, True, 1e-5), (1, 960, 128, 32, True, 1e-5),  # group slab split over 4- / 8-CTA clusters
+    (2, 1280, 64, 32, False, 1e-6), (2, 320, 64, 32, True, 1e-5),  # 2-CTA cluster; 4-byte vectors (10 channels / group)
+    (2, 56, 12, 8, True, 1e-5),   # 7 channels per group: not slab-eligible (odd width) -> stats + apply kernels
 ])
 def test_groupnorm(K, n, c, hw, groups, silu, eps):
     x = rnd(n, c, hw, hw, seed=1) + 0.5  # non-zero mean
