@@ -15,6 +15,17 @@ __device__ __forceinline__ uint32_t pack(float a, float b) {
   return r;
 }
 
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  uint32_t r;
+  asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 template <int MODE>
 __global__ void bench(float* out, long long* cyc, int iters) {
   float x[16];
@@ -43,6 +54,16 @@ __global__ void bench(float* out, long long* cyc, int iters) {
       for (int i = 0; i < 16; ++i) facc += x[i];
 #pragma unroll
       for (int i = 0; i < 16; i += 2) acc ^= pack(x[i], x[i + 1]);
+    } else if (MODE == 5) {  // 8 packed half2 ex2 = 16 exponentials
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = pack_f16(x[2 * i], x[2 * i + 1]) ^ acc;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = ex2_f16x2(h[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc ^= h[i];
     } else if (MODE == 4) {  // 8 packs done with integer ops instead (round-to-nearest-even by hand: 4 ALU ops / pair)
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
@@ -84,5 +105,6 @@ int main() {
   run<2>("16 x EX2 + 8 x F2FP", 24);
   run<3>("16 x (FFMA, EX2, FADD) + 8 x F2FP", 56);
   run<4>("8 x bf16 pack by integer ops", 8);
+  run<5>("8 x F2FP.F16 + 32 x EX2.F16x2 (64 exps)", 40);
   return 0;
 }
