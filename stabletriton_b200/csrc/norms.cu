@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <stdlib.h>
+#include <atomic>
 
 namespace st {
 
@@ -42,7 +43,12 @@ constexpr int kGnMaxThreads = 320;   // >= C/8 for C <= 2560; small CTAs so that
 constexpr int kGnMaxImages = 4096;
 constexpr int kGnStatsPixPerThread = 8;  // 8 x 16 B in flight per thread
 constexpr int kGnApplyPixPerThread = 6;
-__device__ unsigned int g_gn_arrivals[kGnMaxImages];  // per-image tickets; the finalising CTA resets its own
+// Per-image arrival tickets (the finalising CTA resets its own).  Launches on different streams may overlap, so each
+// launch gets its own row of tickets: the host hands out rows round-robin (kGnTicketRows launches would have to be in
+// flight at once for two of them to share one; a row index is baked into the kernel arguments, so every GroupNorm node
+// of a captured graph keeps the row it was captured with).
+constexpr int kGnTicketRows = 256;
+__device__ unsigned int g_gn_arrivals[kGnTicketRows][kGnMaxImages];
 
 struct GnGeom {
   int N, HW, C, G, cpg;
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(kGnMaxThreads, 3)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial,
                 const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                 float* __restrict__ scale_shift, int HW, int C, int G, int cpg, int vecs, int pix_lanes,
-                int pix_per_chunk, float eps) {
+                int pix_per_chunk, float eps, int ticket_row) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_gn[];  // [C] shift | [C] sum(x - shift) | [C] sum((x - shift)^2) | per-thread partials
@@ -191,7 +197,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   // ticket: the last CTA of image n merges all chunks
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&g_gn_arrivals[n], 1u) == static_cast<unsigned>(chunks - 1));
+  if (threadIdx.x == 0) s_last = (atomicAdd(&g_gn_arrivals[ticket_row][n], 1u) == static_cast<unsigned>(chunks - 1));
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -250,7 +256,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
       o[1] = be - mean * sc;
     }
   }
-  if (threadIdx.x == 0) g_gn_arrivals[n] = 0u;
+  if (threadIdx.x == 0) g_gn_arrivals[ticket_row][n] = 0u;
 }
 
 // Pass 3: y = silu?(x * scale + shift), streaming.
@@ -418,10 +424,12 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
     configured = true;
   }
   ST_CHECK_ARG(smem <= 96 * 1024, "groupnorm: C (%d) needs too much shared memory", C);
+  static std::atomic<unsigned> next_ticket_row{0};
+  const int ticket_row = static_cast<int>(next_ticket_row.fetch_add(1, std::memory_order_relaxed) % kGnTicketRows);
   if (dbg != 2)
   launch_kernel(gn_stats_kernel, dim3(g.chunks, N), dim3(g.threads), smem, s, static_cast<const __nv_bfloat16*>(x),
                 partial, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), scale_shift,
-                HW, C, groups, g.cpg, g.vecs, g.pix_lanes, g.pix_per_chunk, eps);
+                HW, C, groups, g.cpg, g.vecs, g.pix_lanes, g.pix_per_chunk, eps, ticket_row);
   ST_CHECK_LAUNCH("gn_stats_kernel");
   const dim3 agrid(g.a_chunks, N);
   if (dbg == 1) return ST_OK;

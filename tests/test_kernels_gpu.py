@@ -65,6 +65,24 @@ def test_groupnorm(K, n, c, hw, groups, silu, eps):
     assert torch.equal(got2, got)
 
 
+def test_groupnorm_launches_on_two_streams_may_overlap(K):
+    """Re-entrancy (no global mutable state shared between calls): every GroupNorm launch has its own
+    arrival tickets, so launches on different streams -- or in parallel branches of one CUDA graph -- may overlap."""
+    xs = [rnd(2, 320, 64, 64, seed=70 + i).cuda().contiguous(memory_format=torch.channels_last) for i in range(2)]
+    w, b = (rnd(320, seed=72) * 0.1 + 1.0).cuda(), (rnd(320, seed=73) * 0.1).cuda()
+    ref = [K.groupnorm_wrapper(x, 32, w, b, 1e-5, True) for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[], []]
+    for _ in range(100):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                outs[i].append(K.groupnorm_wrapper(xs[i], 32, w, b, 1e-5, True))
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert all(torch.equal(o, ref[i]) for o in outs[i])
+
+
 def test_groupnorm_large_mean_is_stable(K):
     x = (rnd(2, 320, 32, 32, seed=4) * 0.5 + 40.0)
     w, b = torch.ones(320, dtype=torch.bfloat16), torch.zeros(320, dtype=torch.bfloat16)
