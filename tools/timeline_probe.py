@@ -67,6 +67,26 @@ def main():
         out["families"][name] = row
         print(f"{name[:34]:34s} {row['launches']:8d} {row['duration_us'] / 1000.0:12.3f} {row['exposed_us'] / 1000.0:11.3f} "
               f"{row['gap_us'] / 1000.0:9.3f}")
+    # the same per kernel instantiation (template arguments kept) and duration class, one replay
+    per = len(evs) // reps
+    one = evs[:per]
+    inst = collections.OrderedDict()
+    prev_end = one[0].time_range.start
+    for e in one:
+        name = e.name.replace("void ", "").replace("st::", "")
+        name = re.sub(r"\(.*", "", name)
+        st_, en = e.time_range.start, e.time_range.end
+        exposed = max(0.0, en - max(st_, prev_end))
+        prev_end = max(prev_end, en)
+        bucket = 1 << max(0, int(exposed).bit_length() - 1)  # power-of-two class of the exposed time (us)
+        d = inst.setdefault((name, bucket), {"launches": 0, "exposed_us": 0.0})
+        d["launches"] += 1
+        d["exposed_us"] += exposed
+    print("\nper instantiation and exposed-time class (one replay):")
+    rows = sorted(inst.items(), key=lambda kv: -kv[1]["exposed_us"])[:40]
+    for (name, bucket), d in rows:
+        print(f"  {name[:70]:70s} ~{bucket:4d} us x {d['launches']:4d}  {d['exposed_us'] / 1000.0:8.3f} ms")
+    out["instantiations"] = [{"kernel": n, "exposed_class_us": b, **d} for (n, b), d in rows]
     if len(sys.argv) > 1:
         with open(sys.argv[1], "w") as f:
             json.dump(out, f, indent=1)
