@@ -323,11 +323,24 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __
                  const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int M, int N,
                  float eps) {
   pdl_launch_dependents();
-  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = N >> 3;
+  // gamma / beta are parameters, not outputs of the preceding kernel: fetch them BEFORE the programmatic dependency
+  // resolves, so that only one memory round trip (the row itself) is left on the exposed path of this latency-bound
+  // kernel (in sequence a LayerNorm launch costs ~5 us, profiles/r01_timeline_v1.txt).  Kept packed: 8 registers / vector.
+  constexpr bool kPrefetch = kVecsPerLane <= 5;  // wide rows: not enough registers, load gamma / beta at their use
+  uint4 gv[kPrefetch ? kVecsPerLane : 1], bv[kPrefetch ? kVecsPerLane : 1];
+#pragma unroll
+  for (int i = 0; i < (kPrefetch ? kVecsPerLane : 0); ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      gv[i] = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
+      bv[i] = beta ? __ldg(reinterpret_cast<const uint4*>(beta + v * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= M) return;
-  const int nvec = N >> 3;
   const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
   float f[kVecsPerLane][8];
   float sum = 0.f;
@@ -364,12 +377,12 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __
     const int v = lane + i * 32;
     if (v < nvec) {
       float g[8], b[8];
-      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), g);
-      if (beta) {
-        unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), b);
+      if (kPrefetch) {
+        unpack8(gv[kPrefetch ? i : 0], g);
+        unpack8(bv[kPrefetch ? i : 0], b);
       } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) b[e] = 0.f;
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), g);
+        unpack8(beta ? __ldg(reinterpret_cast<const uint4*>(beta + v * 8)) : make_uint4(0u, 0u, 0u, 0u), b);
       }
       float o[8];
 #pragma unroll
