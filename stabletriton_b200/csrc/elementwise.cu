@@ -45,39 +45,80 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ state, int lds, c
 }
 
 // ---- tiny-M Linear: one warp per output column, all M rows at once ---------------------------------
+// Weight-bandwidth bound (M <= 32 rows against up to 13 760 x 1280 weights = 35 MB for the batched resnet time-embedding
+// projection).  The weight row of a warp is a parameter, so ALL of its 16-byte loads are issued before the programmatic
+// dependency on the previous kernel resolves (kIters independent loads in flight per lane); the activations -- with
+// SiLU applied once per CTA, not once per output column -- are staged in shared memory as fp32 when they fit.
 constexpr int kSmallMMax = 32;
+constexpr int kSmallMStageFloats = 12 * 1024;  // 48 KB of staged activations (M * K fp32)
+
+// kRows bounds M at compile time: the per-row loops are fully unrolled and predicated, and predicated-off iterations
+// still take issue slots (with a fixed bound of 32 the M = 2 time-embedding projection spent its time issuing them).
+template <int kIters, int kRows>  // 16-byte weight vectors per lane: K <= kIters * 256; M <= kRows
 __global__ void __launch_bounds__(256)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
                       const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy, int M, int N,
-                      int K, int silu_in, int silu_out) {
+                      int K, int silu_in, int silu_out, int stage_x) {
   pdl_launch_dependents();
-  pdl_wait();
+  extern __shared__ float s_x[];  // [M][K] act(x), if stage_x
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (n >= N) return;
-  float acc[kSmallMMax];
+  const bool active = n < N;
+  uint4 wv[kIters];
+  {
+    const __nv_bfloat16* wr = W + static_cast<size_t>(active ? n : 0) * ldw;
 #pragma unroll
-  for (int m = 0; m < kSmallMMax; ++m) acc[m] = 0.f;
-  const __nv_bfloat16* wr = W + static_cast<size_t>(n) * ldw;
-  for (int k = lane * 8; k < K; k += 256) {
-    float wv[8];
-    unpack8e(*reinterpret_cast<const uint4*>(wr + k), wv);
+    for (int i = 0; i < kIters; ++i) {
+      const int k = lane * 8 + i * 256;
+      wv[i] = (active && k < K) ? __ldg(reinterpret_cast<const uint4*>(wr + k)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  pdl_wait();
+  if (stage_x) {
+    for (int i = threadIdx.x * 8; i < M * K; i += blockDim.x * 8) {
+      const int m = i / K, k = i - m * K;  // K % 8 == 0: a vector never straddles two rows
+      float xv[8];
+      unpack8e(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(m) * ldx + k), xv);
 #pragma unroll
-    for (int m = 0; m < kSmallMMax; ++m) {
-      if (m < M) {
-        float xv[8];
-        unpack8e(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(m) * ldx + k), xv);
+      for (int e = 0; e < 8; ++e) s_x[i + e] = silu_in ? silu_f(xv[e]) : xv[e];
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+  float acc[kRows];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xe = silu_in ? silu_f(xv[e]) : xv[e];
-          acc[m] = fmaf(xe, wv[e], acc[m]);
+  for (int m = 0; m < kRows; ++m) acc[m] = 0.f;
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    const int k = lane * 8 + i * 256;
+    if (k < K) {
+      float wf[8];
+      unpack8e(wv[i], wf);
+#pragma unroll
+      for (int m = 0; m < kRows; ++m) {
+        if (m < M) {
+          float xv[8];
+          if (stage_x) {
+            const float4 a = *reinterpret_cast<const float4*>(s_x + m * K + k);
+            const float4 b = *reinterpret_cast<const float4*>(s_x + m * K + k + 4);
+            xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+            xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+          } else {
+            unpack8e(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(m) * ldx + k), xv);
+            if (silu_in) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) xv[e] = silu_f(xv[e]);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[m] = fmaf(xv[e], wf[e], acc[m]);
         }
       }
     }
   }
   const float b = bias ? __bfloat162float(bias[n]) : 0.f;
 #pragma unroll
-  for (int m = 0; m < kSmallMMax; ++m) {
+  for (int m = 0; m < kRows; ++m) {
     if (m < M) {
       float v = acc[m];
 #pragma unroll
@@ -406,9 +447,32 @@ int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const
   ST_CHECK_ARG(N > 0 && K > 0 && K % 8 == 0, "linear_small_m: K (%d) must be a positive multiple of 8", K);
   ST_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0, "linear_small_m: pitches must be multiples of 8");
   ST_CHECK_ARG(aligned16(x) && aligned16(W), "linear_small_m: pointers must be 16-byte aligned");
+  ST_CHECK_ARG(K <= 16 * 256, "linear_small_m: K (%d) must be <= 4096", K);
   const int warps = 8;
-  launch_kernel(linear_small_m_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(W), ldw,
-      static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), ldy, M, N, K, silu_in, silu_out);
+  const int stage_x = static_cast<long>(M) * K <= kSmallMStageFloats ? 1 : 0;
+  const size_t smem = stage_x ? static_cast<size_t>(M) * K * sizeof(float) : 0;
+  const dim3 grid((N + warps - 1) / warps), block(warps * 32);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(W);
+  const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(bias);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  const int iters = (K + 255) / 256;
+#define ST_SMALL_M_LAUNCH(I, R) \
+  launch_kernel(linear_small_m_kernel<I, R>, grid, block, smem, s, xp, ldx, wp, ldw, bp, yp, ldy, M, N, K, silu_in, silu_out, stage_x)
+#define ST_SMALL_M_CASE(I)                  \
+  do {                                      \
+    if (M <= 2) ST_SMALL_M_LAUNCH(I, 2);    \
+    else if (M <= 4) ST_SMALL_M_LAUNCH(I, 4); \
+    else if (M <= 8) ST_SMALL_M_LAUNCH(I, 8); \
+    else ST_SMALL_M_LAUNCH(I, kSmallMMax);  \
+  } while (0)
+  if (iters <= 2) ST_SMALL_M_CASE(2);
+  else if (iters <= 5) ST_SMALL_M_CASE(5);
+  else if (iters <= 11) ST_SMALL_M_CASE(11);
+  else ST_SMALL_M_CASE(16);
+#undef ST_SMALL_M_CASE
+#undef ST_SMALL_M_LAUNCH
   ST_CHECK_LAUNCH("linear_small_m_kernel");
   return ST_OK;
 }

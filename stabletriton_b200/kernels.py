@@ -347,7 +347,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         if temb is not None:
             raise ValueError("conv2d: temb epilogue is only wired for 3x3 convolutions")
         check(L.st_gemm_bf16(xn.data_ptr(), c, wp.data_ptr(), c, out.data_ptr(), k, n * h * w, k, c, _ptr(bias),
-                             res_ptr, k, 0, block_n, stream), "conv1x1")
+                             res_ptr, k, ST_W_STATIC, block_n, stream), "conv1x1")
         return out
 
     if (r, s) != (3, 3) or padding != 1:
@@ -366,7 +366,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
                                              stream), "im2col_smallc")
             out = _empty_nhwc(n, k, h, w, x)
             check(L.st_gemm_bf16(col.data_ptr(), 64, wpad.data_ptr(), 64, out.data_ptr(), k, n * h * w, k, 64,
-                                 _ptr(bias), 0, 0, 0, block_n, stream), "conv_in")
+                                 _ptr(bias), 0, 0, ST_W_STATIC, block_n, stream), "conv_in")
             return out
         # conv_out: pad the K <= 8 output channels to 8, implicit GEMM, then gather the real channels
         if c % 64 != 0 or (h * w) % 128 != 0 and 128 % (h * w) != 0:
@@ -399,7 +399,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         check(L.st_im2col3x3_nhwc_bf16(xn.data_ptr(), col.data_ptr(), n, h, w, c, 2, stream), "im2col")
         out = _empty_nhwc(n, k, ho, wo, x)
         check(L.st_gemm_bf16(col.data_ptr(), 9 * c, wp.data_ptr(), 9 * c, out.data_ptr(), k, n * ho * wo, k, 9 * c,
-                             _ptr(bias), 0, 0, 0, block_n, stream), "conv_s2")
+                             _ptr(bias), 0, 0, ST_W_STATIC, block_n, stream), "conv_s2")
         return out
     if stride != 1:
         raise ValueError("conv2d: stride must be 1 or 2")
