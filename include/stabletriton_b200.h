@@ -66,7 +66,9 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
 /* ---- LayerNorm over the last dimension --------------------------------------------------------
  * Replaces layer_norm(x, weight, bias, eps) (reference: kernels/layer_norm.py:338-346, kernel
  * :114-205; wrapper optimizers/replace_layernorm.py:17-24).  x, y: [M, N] bf16 with row pitch ldx/ldy;
- * gamma/beta: [N] bf16 (beta may be NULL); N % 8 == 0, N <= 4096. */
+ * gamma/beta: [N] bf16 (beta may be NULL); N % 8 == 0, N <= 4096.
+ * gamma / beta are treated as parameters (like W under ST_W_STATIC): they are fetched before the programmatic (PDL)
+ * dependency on the kernel launched just before this one resolves, so they must not be written by that kernel. */
 int st_layernorm_bf16(const void* x, int ldx, void* y, int ldy, const void* gamma, const void* beta, int M, int N,
                       float eps, st_stream_t stream);
 
@@ -87,7 +89,9 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
                  const void* bias, const void* residual, int ldr, unsigned flags, int block_n, st_stream_t stream);
 
 /* Tiny-M Linear (time / added-condition embeddings, M <= 32): y = act_out(act_in(x) . W^T + b).
- * CUDA-core, weight-bandwidth bound.  silu_in applies SiLU to x on load (unet_pt.py:81-82). */
+ * CUDA-core, weight-bandwidth bound.  silu_in applies SiLU to x on load (unet_pt.py:81-82).  W is treated as a
+ * parameter (as under ST_W_STATIC): its rows are requested before the programmatic dependency on the preceding
+ * kernel resolves, so W must not be written by the kernel launched just before this one. */
 int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const void* bias, void* y, int ldy, int M,
                            int N, int K, int silu_in, int silu_out, st_stream_t stream);
 
