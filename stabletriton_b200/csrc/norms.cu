@@ -317,7 +317,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers (two-pass statistics, exact).
 // ------------------------------------------------------------------------------------------------
-template <int kVecsPerLane>
+template <int kVecsPerLane, bool kParamsFirst>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
                  const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int M, int N,
@@ -328,7 +328,9 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __
   // gamma / beta are parameters, not outputs of the preceding kernel: fetch them BEFORE the programmatic dependency
   // resolves, so that only one memory round trip (the row itself) is left on the exposed path of this latency-bound
   // kernel (in sequence a LayerNorm launch costs ~5 us, profiles/r01_timeline_v1.txt).  Kept packed: 8 registers / vector.
-  constexpr bool kPrefetch = kVecsPerLane <= 5;  // wide rows: not enough registers, load gamma / beta at their use
+  // (wide rows: not enough registers; many rows: the kernel is bandwidth-bound and the 40 extra registers would cost a
+  // third of the resident warps -- 65536 x 1280: 5.2 TB/s without, 4.5 TB/s with -- so gamma / beta are loaded at their use)
+  constexpr bool kPrefetch = kParamsFirst && kVecsPerLane <= 5;
   uint4 gv[kPrefetch ? kVecsPerLane : 1], bv[kPrefetch ? kVecsPerLane : 1];
 #pragma unroll
   for (int i = 0; i < (kPrefetch ? kVecsPerLane : 0); ++i) {
@@ -473,9 +475,14 @@ int st_layernorm_bf16(const void* x, int ldx, void* y, int ldy, const void* gamm
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(gamma);
   const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(beta);
-#define ST_LN_CASE(V)                                                                    \
-  case V:                                                                                \
-    launch_kernel(layernorm_kernel<V>, dim3(grid), dim3(256), 0, s, xp, ldx, yp, ldy, gp, bp, M, N, eps);       \
+  // latency-bound launches (a few CTAs per SM: every LayerNorm of the SDXL step at CFG batch 2) fetch gamma / beta first
+  const bool params_first = grid <= 8 * device_sm_count();
+#define ST_LN_CASE(V)                                                                                               \
+  case V:                                                                                                           \
+    if (params_first)                                                                                               \
+      launch_kernel(layernorm_kernel<V, true>, dim3(grid), dim3(256), 0, s, xp, ldx, yp, ldy, gp, bp, M, N, eps);   \
+    else                                                                                                            \
+      launch_kernel(layernorm_kernel<V, false>, dim3(grid), dim3(256), 0, s, xp, ldx, yp, ldy, gp, bp, M, N, eps);  \
     break;
   switch (vpl <= 3 ? 3 : vpl <= 5 ? 5 : vpl <= 8 ? 8 : 16) {
     ST_LN_CASE(3)
