@@ -16,7 +16,12 @@ JSON line keys follow the driver contract; see DESIGN.md "Measurement".
              FLOPs of those launches / their device time, measured live by re-issuing exactly those
              launches in a CUDA graph and timing it with CUDA events on the launching stream
   cpu_baseline  the oracle port of the reference's eager fp32 UNet (oracle/unet_oracle.py) on the host
-             cores at BASELINE config 1 (B=1, 64x64 latent), scaled to the metric's unit by FLOPs
+             cores, on the same workload (CFG batch 2, 128x128 latent), bounded to 2 timed forwards
+  sustained  the same step loop replayed for >= 5 s with its own clock sample (the headline window is < 1 s)
+  strong_scaling  BASELINE configs[3]: 8 prompts x CFG split 8/N per rank, K steps + the NCCL all-gather of the final
+             latents inside the timed region (informational; the headline stays the weak-scaling number)
+  cfg_split  (N = 2 only) one prompt, rank 0 = uncond row, rank 1 = cond row, per-step NCCL all-gather of eps
+             captured inside the step graph
 """
 from __future__ import annotations
 
@@ -77,8 +82,15 @@ def physical_cores() -> int:
     return os.cpu_count() or 1
 
 
-def cpu_reference_times(timed: int, warmup: int):
-    """Seconds per fp32 UNet forward of the oracle port at config 1 (B=1, 4x64x64), all host threads."""
+def workload_name(latent: int, prompts: int) -> str:
+    return (f"SDXL UNet denoise step, {latent * 8}^2, CFG batch 2 x {prompts} prompt(s) per GPU, Euler + guidance 5.0 "
+            f"(BASELINE configs[1])")
+
+
+def cpu_reference_times(timed: int, warmup: int, batch: int = 2, latent: int = 128, small_warmup: bool = False):
+    """Seconds per fp32 UNet forward of the oracle port on the host cores, all host threads.  Default = the workload of
+    the GPU arm itself (BASELINE configs[1]: CFG batch 2, 128x128 latent = 13.52 TFLOP per forward).  small_warmup:
+    one untimed B=1 64x64 forward first (spins up the thread pool and the allocator for a tenth of the cost)."""
     import torch
     from stabletriton_b200 import UNet2DConditionModel, UNetConfig, synth
 
@@ -99,7 +111,10 @@ def cpu_reference_times(timed: int, warmup: int):
         if name.endswith("weight") and "norm" in name:
             t.mul_(0.1).add_(1.0)
         sd[name] = t
-    inp = synth.synth_inputs(1, 64, cfg)
+    inp = synth.synth_inputs(batch, latent, cfg)
+    if small_warmup:
+        w = synth.synth_inputs(1, 64, cfg)
+        oracle.unet_forward(sd, w["sample"], w["timesteps"], w["encoder_hidden_states"], w["added_cond_kwargs"])
     times = []
     for i in range(warmup + timed):
         t0 = time.perf_counter()
@@ -111,22 +126,29 @@ def cpu_reference_times(timed: int, warmup: int):
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (its eager fp32 UNet, restated bit-exactly by the oracle
+    port: tests/test_oracle.py) on the box's host cores, on the SAME workload as the GPU arm: one CFG-batch-2 forward
+    of the full SDXL UNet at a 128x128 latent per step.  A forward costs 13.5 TFLOP in fp32 (~10-40 s on 8-32 cores),
+    so the run is bounded to 1 warm-up + at most 3 timed steps whatever --steps asks for; `steps`/`warmup` in the line
+    are what was actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     timed = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
-    times, cores = cpu_reference_times(timed, warm)
-    sec = statistics.median(times)
-    value = (1.0 / sec) * (FLOPS_CONFIG1 / FLOPS_CONFIG2)  # config-2-equivalent it/s, scaled by FLOPs
-    sample = (f"oracle port of reference eager fp32 UNet, B=1 4x64x64 (BASELINE config 1), {timed} timed forwards "
-              f"(median {sec:.2f} s each, {FLOPS_CONFIG1 / sec / 1e12:.3f} TFLOP/s), scaled to config 2 by FLOPs "
-              f"(x{FLOPS_CONFIG1 / FLOPS_CONFIG2:.4f})")
+    times, cores = cpu_reference_times(timed, warm, batch=2 * args.prompts, latent=args.latent)
+    sec = statistics.mean(times)
+    value = args.prompts / sec
+    flops = FLOPS_CONFIG2 * args.prompts * (args.latent / 128.0) ** 2
+    sample = (f"oracle port of the reference eager fp32 UNet (optimizers/unet_pt.py), CFG batch {2 * args.prompts}, "
+              f"4x{args.latent}x{args.latent} latent (BASELINE configs[1], the GPU arm's own workload), {warm} warm-up + "
+              f"{timed} timed forwards, mean {sec:.2f} s each (~{flops / sec / 1e12:.2f} TFLOP/s), {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
-        "warmup": warm, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1000.0 * sec, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SDXL UNet denoise step, 1024^2, CFG batch 2 (CPU arm timed at config 1 and scaled)"},
+        "config": {"workload": workload_name(args.latent, args.prompts), "prompts_per_gpu": args.prompts,
+                   "latent": args.latent, "arm": "reference eager fp32 path on the host CPU, same workload as the GPU arm"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -313,6 +335,119 @@ def run_gpu_arm(args):
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- informational: sustained -- whole 30-step images back to back for >= --sustained-seconds -----------
+    sustained = None
+    if args.sustained_seconds > 0:
+        per_image = 30
+        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every rank must run the same number of images
+        images = max(1, int(args.sustained_seconds * 1000.0 / (t.item() / steps * per_image) + 0.999))
+        sus_sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sus_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        noise0 = inp["sample"].float()
+        barrier()
+        s0.record()
+        for _ in range(images):
+            loop.reset(noise0)
+            for _ in range(per_image):
+                loop.run_step()
+        s1.record()
+        barrier()
+        ms_sus = s0.elapsed_time(s1)
+        sus_clocks = sus_sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms_sus], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_sus = t.item()
+        sustained = {"value": world * prompts * images * per_image / (ms_sus * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms_sus / (images * per_image), "steps": images * per_image, "seconds": ms_sus * 1e-3,
+                     "images_per_s_30_steps": world * prompts * images / (ms_sus * 1e-3), "clocks": sus_clocks,
+                     "note": "same step graph as `value`, 30-step images back to back (loop state reset between images)"}
+    del loop
+
+    # ---- informational: strong scaling (BASELINE configs[3]) -- 8 prompts x CFG split over the ranks ------------
+    strong = None
+    if args.prompts_total > 0:
+        from stabletriton_b200.pipeline import gather_latents, shard_prompts
+        total = args.prompts_total
+        lo, hi = shard_prompts(total, world, rank)
+        local_n = hi - lo
+        k_steps = min(steps, 30)
+        all_c = synth.synth_inputs(total, latent, cfg, seed=2024, device=device, dtype=torch.bfloat16)
+        all_u = synth.synth_inputs(total, latent, cfg, seed=2025, device=device, dtype=torch.bfloat16)
+        pick = lambda d: {"encoder_hidden_states": d["encoder_hidden_states"][lo:hi],  # noqa: E731
+                          **{k: v[lo:hi] for k, v in d["added_cond_kwargs"].items()}}
+        noise = all_c["sample"][lo:hi].float()
+        if local_n > 0:
+            sl = DenoiseLoop(compiled, prompts=local_n, latent_hw=latent, num_steps=max(k_steps + warmup, 30),
+                             device=device, hoist_prompt_constants=False)
+            sl.set_conditioning(pick(all_c), pick(all_u))
+            sl.reset(noise)
+            sl.capture()
+            sl.reset(noise)
+            for _ in range(warmup):
+                sl.run_step()
+        empty = torch.zeros((0, cfg.in_channels, latent, latent), dtype=torch.bfloat16, device=device)
+        gather_latents(sl.x.to(torch.bfloat16) if local_n > 0 else empty, total)  # NCCL communicator warm-up
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        if local_n > 0:
+            for _ in range(k_steps):
+                sl.run_step()
+        final = gather_latents(sl.x.to(torch.bfloat16) if local_n > 0 else empty, total)
+        g1.record()
+        barrier()
+        ms_strong = g0.elapsed_time(g1)
+        assert final.shape[0] == total
+        if world > 1:
+            t = torch.tensor([ms_strong], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_strong = t.item()
+        strong = {"value": total * k_steps / (ms_strong * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "prompts_total": total, "prompts_per_gpu": (total + world - 1) // world, "steps": k_steps,
+                  "ms_per_step": ms_strong / k_steps, "images_per_s_30_steps": total * k_steps / 30.0 / (ms_strong * 1e-3),
+                  "collective": (f"one NCCL all_gather_into_tensor of the final latents, {total} x "
+                                 f"{cfg.in_channels * latent * latent * 2} B bf16, inside the timed region"
+                                 if world > 1 else "none (single rank)"),
+                  "unit_note": "it = one CFG-batch-2 UNet forward + scheduler step of one prompt"}
+        if local_n > 0:
+            del sl
+
+    # ---- informational: CFG split over 2 GPUs (one prompt; per-step all-gather of eps inside the step graph) ----
+    cfg_split = None
+    if world == 2 and not args.no_cfg_split:
+        one_c = synth.synth_inputs(1, latent, cfg, seed=2024, device=device, dtype=torch.bfloat16)
+        one_u = synth.synth_inputs(1, latent, cfg, seed=2025, device=device, dtype=torch.bfloat16)
+        as_cond = lambda d: {"encoder_hidden_states": d["encoder_hidden_states"], **d["added_cond_kwargs"]}  # noqa: E731
+        cl = DenoiseLoop(compiled, prompts=1, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device,
+                         cfg_row=rank, hoist_prompt_constants=False)
+        cl.set_conditioning(as_cond(one_c), as_cond(one_u))
+        cl.reset(one_c["sample"].float())
+        cl.capture()
+        cl.reset(one_c["sample"].float())
+        for _ in range(warmup):
+            cl.run_step()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        c0.record()
+        for _ in range(steps):
+            cl.run_step()
+        c1.record()
+        barrier()
+        t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_split = t.item()
+        cfg_split = {"value": steps / (ms_split * 1e-3), "unit": UNIT, "ms_per_step": ms_split / steps, "prompts": 1,
+                     "collective": f"NCCL all_gather_into_tensor of eps per step, 2 x {cfg.out_channels * latent * latent * 2}"
+                                   f" B, captured in the step graph",
+                     "note": "latency mode: ONE prompt on two GPUs (rank 0 = uncond row, rank 1 = cond row)"}
+        del cl
+
     # ---- max over ranks -------------------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e, ms_hoisted], dtype=torch.float64, device=device)
@@ -366,13 +501,14 @@ def run_gpu_arm(args):
         # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # the contract asks for it at N=1 only (torchrun also pins OMP to 1 thread)
-            times, cores = cpu_reference_times(timed=2, warmup=1)
-            sec = statistics.median(times)
+            times, cores = cpu_reference_times(timed=2, warmup=0, batch=2 * prompts, latent=latent, small_warmup=True)
+            sec = statistics.mean(times)
+            flops = FLOPS_CONFIG2 * prompts * (latent / 128.0) ** 2
             cpu = {
-                "value": (1.0 / sec) * (FLOPS_CONFIG1 / FLOPS_CONFIG2), "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": (f"oracle port of the reference eager fp32 UNet at BASELINE config 1 (B=1, 4x64x64), 2 timed "
-                           f"forwards, median {sec:.2f} s ({FLOPS_CONFIG1 / sec / 1e12:.3f} TFLOP/s), scaled to "
-                           f"config 2 by FLOPs"),
+                "value": prompts / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": (f"oracle port of the reference eager fp32 UNet on the same workload (CFG batch {2 * prompts}, "
+                           f"4x{latent}x{latent} latent): 2 timed forwards after one small warm-up forward, mean "
+                           f"{sec:.2f} s each (~{flops / sec / 1e12:.2f} TFLOP/s), {cores} threads"),
             }
         value = world * prompts * steps / (ms_total * 1e-3)
         e2e_value = world * prompts * steps / (ms_e2e * 1e-3)
@@ -381,8 +517,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": f"SDXL UNet denoise step, {latent * 8}^2, CFG batch 2 x {prompts} prompt(s) per GPU, "
-                            f"Euler + guidance 5.0, CUDA graph (BASELINE configs[1])",
+                "workload": workload_name(latent, prompts), "execution": "one CUDA-graph replay per step",
                 "prompts_per_gpu": prompts, "latent": latent, "parallelism": f"dp{world}",
                 "l2": "no explicit flush: every step streams 5.1 GB of bf16 weights (> 126 MB L2)",
                 "weights": "random-init (hash-seeded), Diffusers SDXL-base architecture, 2.567 B params",
@@ -395,6 +530,9 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "sustained": sustained,
+            "strong_scaling": strong,
+            "cfg_split": cfg_split,
             "prompt_constants_hoisted": {
                 "ms_per_step": ms_hoisted / steps, "value": world * prompts * steps / (ms_hoisted * 1e-3), "unit": UNIT,
                 "note": "not the headline: cross-attention K/V projections + text/time-ids embedding computed once per "
@@ -446,6 +584,9 @@ def main():
     ap.add_argument("--latent", type=int, default=128, help="latent side (128 = 1024^2)")
     ap.add_argument("--prompts", type=int, default=1, help="prompts per GPU (each is a CFG pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=5.0, help="length of the informational sustained run (0: skip)")
+    ap.add_argument("--prompts-total", type=int, default=8, help="strong-scaling arm: prompts split over all ranks (0: skip)")
+    ap.add_argument("--no-cfg-split", action="store_true", help="skip the 2-GPU CFG-split arm")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -89,11 +89,11 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
                  const void* bias, const void* residual, int ldr, unsigned flags, int block_n, st_stream_t stream);
 
 /* Tiny-M Linear (time / added-condition embeddings, M <= 32): y = act_out(act_in(x) . W^T + b).
- * CUDA-core, weight-bandwidth bound.  silu_in applies SiLU to x on load (unet_pt.py:81-82).  W is treated as a
- * parameter (as under ST_W_STATIC): its rows are requested before the programmatic dependency on the preceding
- * kernel resolves, so W must not be written by the kernel launched just before this one. */
+ * CUDA-core, weight-bandwidth bound.  silu_in applies SiLU to x on load (unet_pt.py:81-82).  flags: ST_W_STATIC
+ * declares W a parameter (not written by the kernel launched just before this one): its rows are then requested
+ * before the programmatic dependency on the preceding kernel resolves; without the flag W is read after it. */
 int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const void* bias, void* y, int ldy, int M,
-                           int N, int K, int silu_in, int silu_out, st_stream_t stream);
+                           int N, int K, int silu_in, int silu_out, unsigned flags, st_stream_t stream);
 
 /* ---- 3x3 convolution, pad 1, stride 1, NHWC, implicit GEMM on tcgen05 --------------------------
  * Replaces implicit_gemm_fprop(a NHWC, b KRSC) (reference: kernels/Conv_Kernels/conv_implicit_gemm.py:

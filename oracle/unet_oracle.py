@@ -50,7 +50,7 @@ def _count(sd: SD, prefix: str) -> int:
 def timesteps_embedding(t: torch.Tensor, num_channels: int) -> torch.Tensor:
     """optimizers/unet_pt.py:22-36 -- cat([cos, sin]) of t * exp(-ln(1e4) * i / half)."""
     half = num_channels // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - 0.0)
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / (half - 0.0)
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
@@ -198,7 +198,7 @@ def unet_forward(sd: SD, sample, timesteps, encoder_hidden_states, added_cond_kw
     ctx = encoder_hidden_states.float()
     base = sd["conv_in.weight"].shape[0]
 
-    t = timesteps.expand(sample.shape[0])
+    t = timesteps.to(sample.device).expand(sample.shape[0])  # device-agnostic: the GPU parity tests run this file in fp32 on cuda
     emb = timestep_mlp(_sub(sd, "time_embedding"), timesteps_embedding(t, base))
     text_embeds = added_cond_kwargs["text_embeds"].float()
     time_ids = added_cond_kwargs["time_ids"].float()

@@ -733,8 +733,10 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   if (rc != ST_OK) return rc;
   rc = make_tmap_bhtd(&tv, v, B, H, Tk, v_sb, v_sh, v_st);
   if (rc != ST_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per context: once per device, not per process
+  const int dev = current_device();
+  ST_CHECK_ARG(dev >= 0, "attention: device ordinal outside [0, %d)", kMaxDevices);
+  if (!configured.done(dev)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
     if (e != cudaSuccess) {
@@ -753,7 +755,7 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
     }
-    configured = true;
+    configured.mark(dev);
   }
   AttnParams p;
   p.O = static_cast<__nv_bfloat16*>(o);

@@ -11,7 +11,7 @@
 namespace st {
 
 static thread_local char g_error[512] = "";
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,7 +20,20 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-unsigned long long* launch_counter() { return &g_launches; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return (dev >= 0 && dev < kMaxDevices) ? dev : -1;
+}
+
+bool PerDeviceOnce::done(int dev) const {
+  return dev >= 0 && ((__atomic_load_n(&mask_, __ATOMIC_ACQUIRE) >> dev) & 1ull) != 0;
+}
+void PerDeviceOnce::mark(int dev) {
+  if (dev >= 0) __atomic_fetch_or(&mask_, 1ull << dev, __ATOMIC_RELEASE);
+}
 
 bool pdl_enabled() {
   static const bool on = [] {
@@ -31,16 +44,15 @@ bool pdl_enabled() {
 }
 
 int device_sm_count() {
-  static int cached[64] = {0};
+  static int cached[kMaxDevices] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (cached[dev] == 0) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    cached[dev] = n;
-  }
-  return cached[dev];
+  const bool cacheable = dev >= 0 && dev < kMaxDevices;
+  if (cacheable && cached[dev] != 0) return cached[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (cacheable) cached[dev] = n;  // benign race: every writer stores the same value
+  return n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -111,7 +123,7 @@ extern "C" {
 
 int st_version(void) { return ST_VERSION; }
 const char* st_last_error_string(void) { return st::g_error; }
-unsigned long long st_launch_count(void) { return st::g_launches; }
-void st_reset_launch_count(void) { st::g_launches = 0; }
+unsigned long long st_launch_count(void) { return st::g_launches.load(std::memory_order_relaxed); }
+void st_reset_launch_count(void) { st::g_launches.store(0, std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -14,7 +14,20 @@ namespace st {
 
 void set_error(const char* fmt, ...);
 int device_sm_count();
-unsigned long long* launch_counter();
+void count_launch();  // atomic: entry points may be called from several host threads (one per device)
+
+// Ordinal of the calling thread's current device, or -1 if it is outside [0, kMaxDevices) -- per-device state is
+// never aliased onto slot 0.
+constexpr int kMaxDevices = 64;
+int current_device();
+
+// One-time per-DEVICE set-up (cudaFuncSetAttribute applies to the current context only): `done(dev)` is false until
+// `mark(dev)`; the guarded work is idempotent, so two threads racing on the same device merely repeat it.
+struct PerDeviceOnce {
+  bool done(int dev) const;
+  void mark(int dev);
+  unsigned long long mask_ = 0;  // accessed with atomic builtins
+};
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with row pitch ld (elements);
 // box = [box_rows, 64 cols], 128-byte swizzle.  Returns 0 on success.
@@ -80,7 +93,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
       st::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));         \
       return ST_ERR_CUDA;                                                            \
     }                                                                                \
-    ++*st::launch_counter();                                                         \
+    st::count_launch();                                                              \
   } while (0)
 
 }  // namespace st

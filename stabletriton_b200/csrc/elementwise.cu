@@ -58,8 +58,9 @@ template <int kIters, int kRows>  // 16-byte weight vectors per lane: K <= kIter
 __global__ void __launch_bounds__(256)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
                       const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy, int M, int N,
-                      int K, int silu_in, int silu_out, int stage_x) {
+                      int K, int silu_in, int silu_out, int stage_x, int w_static) {
   pdl_launch_dependents();
+  if (!w_static) pdl_wait();  // W may be the output of the preceding kernel: no loads ahead of the dependency
   extern __shared__ float s_x[];  // [M][K] act(x), if stage_x
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -73,7 +74,7 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_b
       wv[i] = (active && k < K) ? __ldg(reinterpret_cast<const uint4*>(wr + k)) : make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  pdl_wait();
+  if (w_static) pdl_wait();
   if (stage_x) {
     for (int i = threadIdx.x * 8; i < M * K; i += blockDim.x * 8) {
       const int m = i / K, k = i - m * K;  // K % 8 == 0: a vector never straddles two rows
@@ -440,9 +441,10 @@ int st_geglu_bf16(const void* state, int ld_state, const void* gate, int ld_gate
 }
 
 int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const void* bias, void* y, int ldy, int M,
-                           int N, int K, int silu_in, int silu_out, st_stream_t stream) {
+                           int N, int K, int silu_in, int silu_out, unsigned flags, st_stream_t stream) {
   using namespace st;
   ST_CHECK_ARG(x && W && y, "linear_small_m: null pointer");
+  const int w_static = (flags & ST_W_STATIC) ? 1 : 0;
   ST_CHECK_ARG(M > 0 && M <= kSmallMMax, "linear_small_m: M (%d) must be in [1, %d]", M, kSmallMMax);
   ST_CHECK_ARG(N > 0 && K > 0 && K % 8 == 0, "linear_small_m: K (%d) must be a positive multiple of 8", K);
   ST_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0, "linear_small_m: pitches must be multiples of 8");
@@ -459,7 +461,7 @@ int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   const int iters = (K + 255) / 256;
 #define ST_SMALL_M_LAUNCH(I, R) \
-  launch_kernel(linear_small_m_kernel<I, R>, grid, block, smem, s, xp, ldx, wp, ldw, bp, yp, ldy, M, N, K, silu_in, silu_out, stage_x)
+  launch_kernel(linear_small_m_kernel<I, R>, grid, block, smem, s, xp, ldx, wp, ldw, bp, yp, ldy, M, N, K, silu_in, silu_out, stage_x, w_static)
 #define ST_SMALL_M_CASE(I)                  \
   do {                                      \
     if (M <= 2) ST_SMALL_M_LAUNCH(I, 2);    \
@@ -491,10 +493,12 @@ int st_conv3x3_direct_bf16(const void* x, long long xs_n, long long xs_h, long l
     ST_CHECK_ARG(aligned16(y) && (!bias || aligned16(bias)), "conv3x3_direct: y/bias must be 16-byte aligned");
     const size_t smem = static_cast<size_t>(9) * C * K * sizeof(float);
     ST_CHECK_ARG(smem <= 96 * 1024, "conv3x3_direct: weights do not fit in shared memory");
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    const int dev = current_device();
+    ST_CHECK_ARG(dev >= 0, "conv3x3_direct: device ordinal outside [0, %d)", kMaxDevices);
+    if (!configured.done(dev)) {
       cudaFuncSetAttribute(conv3x3_small_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      configured = true;
+      configured.mark(dev);
     }
     const long long total = static_cast<long long>(N) * H * W * (K / 8);
     launch_kernel(conv3x3_small_c_kernel, dim3(grid_for(total, 256, 4)), dim3(256), smem, s, static_cast<const __nv_bfloat16*>(x), xs_n, xs_h, xs_w, xs_c, static_cast<const __nv_bfloat16*>(w),
@@ -509,11 +513,13 @@ int st_conv3x3_direct_bf16(const void* x, long long xs_n, long long xs_h, long l
   ST_CHECK_ARG(aligned16(x) && aligned16(w), "conv3x3_direct: x/w must be 16-byte aligned");
   const size_t smem = static_cast<size_t>(K) * 9 * C * 2;
   ST_CHECK_ARG(smem <= 96 * 1024 && (K * 9 * C) % 8 == 0, "conv3x3_direct: weights do not fit in shared memory");
-  static bool configured_k = false;
-  if (!configured_k) {
+  static PerDeviceOnce configured_k;
+  const int dev_k = current_device();
+  ST_CHECK_ARG(dev_k >= 0, "conv3x3_direct: device ordinal outside [0, %d)", kMaxDevices);
+  if (!configured_k.done(dev_k)) {
     cudaFuncSetAttribute(conv3x3_small_k_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(conv3x3_small_k_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    configured_k = true;
+    configured_k.mark(dev_k);
   }
   const long long pixels = static_cast<long long>(N) * H * W;
   const int grid = grid_for(pixels * 32, 256, 4);

@@ -74,14 +74,19 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                        cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES, kCluster>;
   auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu, kStreamK, kCluster>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation AND per device (function attributes live in the context)
+  const int dev = current_device();
+  if (dev < 0) {
+    set_error("gemm: device ordinal outside [0, %d)", kMaxDevices);
+    return ST_ERR_INVALID_ARGUMENT;
+  }
+  if (!configured.done(dev)) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("gemm: cudaFuncSetAttribute(%d bytes) failed: %s", S::kTotal, cudaGetErrorString(e));
       return ST_ERR_CUDA;
     }
-    configured = true;
+    configured.mark(dev);
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const long units = static_cast<long>(tiles) * (p.K / kGemmBlockK);
@@ -129,16 +134,10 @@ static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 static unsigned long long* g_gemm_trace = nullptr;  // debug only, see st_debug_set_gemm_trace
 
 // stream-K state: caller-provided fp32 scratch (st_set_workspace) and self-resetting arrival flags
-constexpr int kMaxDevices = 16;
 static void* g_ws_ptr[kMaxDevices] = {nullptr};
 static size_t g_ws_bytes[kMaxDevices] = {0};
+static unsigned* g_sk_flag_ptr[kMaxDevices] = {nullptr};  // address of g_sk_flags in each device's context
 __device__ unsigned g_sk_flags[256 * 32];  // one flag per 128-byte line
-
-static int current_device() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
-}
 
 // Decide whether a GEMM with `tiles` 128x256 tiles and `nkb` k-blocks should run stream-K: only when the
 // tiles do not fill the machine and the K loop is long enough to pay for the fix-up (cycle model as above).
@@ -152,16 +151,15 @@ static bool want_stream_k(long tiles256, int nkb, long tiles_chosen, float** ws,
   }();
   const int sms = device_sm_count();
   const int dev = current_device();
-  if (disabled || !g_ws_ptr[dev] || tiles256 >= sms || tiles_chosen > sms || nkb < 16) return false;
+  if (disabled || dev < 0 || !g_ws_ptr[dev] || tiles256 >= sms || tiles_chosen > sms || nkb < 16) return false;
   if (g_ws_bytes[dev] < static_cast<size_t>(sms) * kGemmBlockM * 256 * sizeof(float)) return false;
   const double cost_plain = 554.0 * nkb + 6000.0;
   const double cost_sk = 554.0 * ((tiles256 * nkb + sms - 1) / sms) + 10000.0;
   if (cost_sk > 0.85 * cost_plain) return false;
-  static unsigned* flag_ptr = nullptr;
-  if (!flag_ptr) cudaGetSymbolAddress(reinterpret_cast<void**>(&flag_ptr), g_sk_flags);
+  if (!g_sk_flag_ptr[dev]) cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sk_flag_ptr[dev]), g_sk_flags);
   *ws = static_cast<float*>(g_ws_ptr[dev]);
-  *flags = flag_ptr;
-  return flag_ptr != nullptr;
+  *flags = g_sk_flag_ptr[dev];
+  return g_sk_flag_ptr[dev] != nullptr;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -317,6 +315,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
 
 int st_set_workspace(void* ptr, size_t bytes) {
   const int dev = st::current_device();
+  ST_CHECK_ARG(dev >= 0, "set_workspace: device ordinal outside [0, %d)", st::kMaxDevices);
   st::g_ws_ptr[dev] = ptr;
   st::g_ws_bytes[dev] = ptr ? bytes : 0;
   return ST_OK;

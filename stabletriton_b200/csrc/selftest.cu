@@ -498,7 +498,7 @@ static void test_misc() {
     __nv_bfloat16* b = dev_bf16(N, 0.5f, &hb);
     __nv_bfloat16* y;
     CK(cudaMalloc(&y, (size_t)M * N * 2));
-    ST(st_linear_small_m_bf16(x, K, w, K, b, y, N, M, N, K, 1, 1, 0));
+    ST(st_linear_small_m_bf16(x, K, w, K, b, y, N, M, N, K, 1, 1, ST_W_STATIC, 0));
     CK(cudaDeviceSynchronize());
     std::vector<float> ref((size_t)M * N);
     for (int m = 0; m < M; ++m)

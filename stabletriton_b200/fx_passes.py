@@ -97,6 +97,60 @@ _MUL = (operator.mul, torch.mul)
 
 
 # ------------------------------------------------------------------------------------------------
+# fused parameter buffers stay LIVE
+# ------------------------------------------------------------------------------------------------
+# The fusion passes below row-concatenate the weights of several Linears into one buffer (QKV, all cross-attention K/V
+# projections, all resnet time-embedding projections).  A plain copy would freeze the weights at compile() time: a
+# later in-place update (load_state_dict, a LoRA merge, `weight.copy_`) would change the un-fused Linears but not the
+# attention / time-embedding projections.  So every fused buffer records where its rows came from
+# (`gm._st_fused_sources`), and `alias_fused_parameters_` makes the buffer the storage of those parameters: each
+# module's weight / bias becomes a row-slice view of it, so in-place updates reach the kernels with no copy -- also
+# through an already captured CUDA graph, which reads the same addresses.  Updates that REPLACE a parameter tensor
+# (load_state_dict(assign=True), `module.weight = ...`) break the aliasing; `refresh_fused_parameters_` copies the
+# current parameter values back into the buffers (in place) and re-establishes it.
+def _record_fused(gm: fx.GraphModule, buffer: str, parts: List[Tuple[str, str, int, int]]) -> None:
+    """parts: (module qualified name, 'weight' | 'bias', first row in the buffer, rows)."""
+    if not hasattr(gm, "_st_fused_sources"):
+        gm._st_fused_sources = {}
+    gm._st_fused_sources[buffer] = list(parts)
+
+
+def alias_fused_parameters_(gm: fx.GraphModule) -> int:
+    """Re-point every parameter that was copied into a fused buffer at its rows of that buffer.  Returns the number
+    of parameters aliased."""
+    n = 0
+    with torch.no_grad():
+        for buffer, parts in getattr(gm, "_st_fused_sources", {}).items():
+            buf = gm.get_buffer(buffer)
+            for qualname, attr, off, rows in parts:
+                param = getattr(gm.get_submodule(qualname), attr)
+                view = buf[off:off + rows]
+                if param.data_ptr() != view.data_ptr() or param.device != view.device:
+                    if param.shape != view.shape or param.dtype != view.dtype:
+                        raise ValueError(f"fused buffer {buffer}: {qualname}.{attr} changed shape or dtype")
+                    param.data = view
+                n += 1
+    return n
+
+
+def refresh_fused_parameters_(gm: fx.GraphModule) -> int:
+    """Copy the CURRENT value of every fused parameter into its buffer (in place: captured graphs keep reading the same
+    addresses) and re-alias it.  Needed only after a parameter tensor was replaced instead of updated in place."""
+    n = 0
+    with torch.no_grad():
+        for buffer, parts in getattr(gm, "_st_fused_sources", {}).items():
+            buf = gm.get_buffer(buffer)
+            for qualname, attr, off, rows in parts:
+                param = getattr(gm.get_submodule(qualname), attr)
+                view = buf[off:off + rows]
+                if param.data_ptr() != view.data_ptr():
+                    view.copy_(param.detach().to(device=view.device, dtype=view.dtype))
+                    n += 1
+    alias_fused_parameters_(gm)
+    return n
+
+
+# ------------------------------------------------------------------------------------------------
 # passes
 # ------------------------------------------------------------------------------------------------
 def remove_dropout(gm: fx.GraphModule) -> int:
@@ -192,6 +246,11 @@ def fuse_qkv_projection(gm: fx.GraphModule) -> int:
         with torch.no_grad():
             gm.register_buffer(name, torch.cat([m.weight.detach() for _, m in group], dim=0).contiguous(),
                                persistent=False)
+        parts, row = [], 0
+        for node, m in group:
+            parts.append((node.target, "weight", row, m.out_features))
+            row += m.out_features
+        _record_fused(gm, name, parts)
         first = group[0][0]
         with gm.graph.inserting_before(att):
             w = gm.graph.get_attr(name)
@@ -226,6 +285,12 @@ def fuse_shared_input_projections(gm: fx.GraphModule) -> int:
         name = f"_st_shared_proj_{n}"
         with torch.no_grad():
             gm.register_buffer(name, torch.cat(weights, dim=0).contiguous(), persistent=False)
+        parts, row = [], 0
+        for x, wt in zip(nodes, weights):  # the per-layer buffers' sources move into the shared buffer
+            for qualname, attr, off, rows in getattr(gm, "_st_fused_sources", {}).get(x.args[1].target, []):
+                parts.append((qualname, attr, row + off, rows))
+            row += wt.shape[0]
+        _record_fused(gm, name, parts)
         first = nodes[0]
         with gm.graph.inserting_before(first):
             w = gm.graph.get_attr(name)
@@ -243,6 +308,7 @@ def fuse_shared_input_projections(gm: fx.GraphModule) -> int:
     for name in [k for k, _ in gm.named_buffers() if k.startswith("_st_fused_proj_")]:
         if not any(nd.op == "get_attr" and nd.target == name for nd in gm.graph.nodes):
             delattr(gm, name)
+            getattr(gm, "_st_fused_sources", {}).pop(name, None)
     return n
 
 
@@ -266,6 +332,13 @@ def fuse_time_embedding_projections(gm: fx.GraphModule) -> int:
         with torch.no_grad():
             gm.register_buffer(wname, torch.cat([m.weight.detach() for m in mods], dim=0).contiguous(), persistent=False)
             gm.register_buffer(bname, torch.cat([m.bias.detach() for m in mods], dim=0).contiguous(), persistent=False)
+        wparts, bparts, row = [], [], 0
+        for x, m in zip(nodes, mods):
+            wparts.append((x.target, "weight", row, m.out_features))
+            bparts.append((x.target, "bias", row, m.out_features))
+            row += m.out_features
+        _record_fused(gm, wname, wparts)
+        _record_fused(gm, bname, bparts)
         first = min(nodes, key=lambda x: list(gm.graph.nodes).index(x))
         with gm.graph.inserting_before(first):
             w, b = gm.graph.get_attr(wname), gm.graph.get_attr(bname)

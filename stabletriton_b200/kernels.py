@@ -154,12 +154,15 @@ SMALL_M = 32
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, activation: bool = False,
            residual: Optional[torch.Tensor] = None, geglu: bool = False, silu_input: bool = False,
-           block_n: int = 0) -> torch.Tensor:
+           block_n: int = 0, w_static: bool = False) -> torch.Tensor:
     """y = epi(x @ weight.T + bias) [+ residual]; weight is (N, K) as in nn.Linear.
 
     activation: SiLU epilogue.  geglu: weight rows are [state ; gate], y = state * gelu(gate) with N/2
     columns.  residual (same shape as y) is added in fp32 before the single bf16 rounding.
     silu_input applies SiLU to x on load (tiny-M path only: the resnet time-embedding projection).
+    w_static: the caller vouches that `weight` is a parameter -- not produced by the kernel launched just before this
+    one -- so the kernel may fetch it ahead of its programmatic (PDL) dependency (ST_W_STATIC).  The op seam
+    (wrappers.py) sets it for module parameters; it is dropped again if this call has to copy the weight first.
     """
     _require_bf16_cuda("linear", x, weight, bias, residual)
     _ensure_workspace(x.device)
@@ -170,13 +173,15 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         raise ValueError(f"linear: x has {x.shape[-1]} features, weight expects {k}")
     if weight.stride(1) != 1:
         weight = weight.contiguous()
+        w_static = False  # the copy is produced on this stream, right before the launch
+    wflag = ST_W_STATIC if w_static else 0
     xr, m, lda = _rows(x)
     n_out = n_rows // 2 if geglu else n_rows
     out = torch.empty(x.shape[:-1] + (n_out,), dtype=BF16, device=x.device)
     L = lib()
     if m <= SMALL_M and not geglu and residual is None:
         check(L.st_linear_small_m_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias),
-                                       out.data_ptr(), n_out, m, n_rows, k, int(silu_input), int(activation),
+                                       out.data_ptr(), n_out, m, n_rows, k, int(silu_input), int(activation), wflag,
                                        _stream(x)), "linear_small_m")
         return out
     if silu_input:
@@ -188,9 +193,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         rr, _, ldr = _rows(residual)
         res_ptr = rr.data_ptr()
         residual = rr  # keep alive
-    # weights are parameters, never the output of the kernel launched just before: let the GEMM start
-    # streaming them ahead of the PDL dependency (ST_W_STATIC)
-    flags = (ST_EPI_SILU if activation else 0) | (ST_EPI_GEGLU if geglu else 0) | ST_W_STATIC
+    flags = (ST_EPI_SILU if activation else 0) | (ST_EPI_GEGLU if geglu else 0) | wflag
     check(L.st_gemm_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), out.data_ptr(), n_out, m, n_rows, k,
                          _ptr(bias), res_ptr, ldr, flags, block_n, _stream(x)), "gemm")
     return out
@@ -275,18 +278,41 @@ _PADDED: dict = {}  # id(tensor) -> (weakref to the tensor, {tag: (version, padd
 def _padded(t: torch.Tensor, tag: str, make):
     """Zero-padded copy of a (tiny) weight / bias, built once per tensor object + version and reused -- the
     first call happens during warm-up, so CUDA-graph capture only ever sees the cached tensor.  Keyed by the
-    identity of the live tensor object (a data_ptr key could alias a freed tensor of another model)."""
+    identity of the live tensor object (a data_ptr key could alias a freed tensor of another model).
+    Returns (copy, fresh): fresh = the copy was produced by THIS call (on the current stream)."""
     key = id(t)
     entry = _PADDED.get(key)
     if entry is None or entry[0]() is not t:
         entry = (weakref.ref(t, lambda _r, k=key: _PADDED.pop(k, None)), {})
         _PADDED[key] = entry
     hit = entry[1].get(tag)
-    if hit is None or hit[0] != t._version:
+    fresh = hit is None or hit[0] != t._version
+    if fresh:
         with torch.no_grad():
-            hit = (t._version, make())
+            new = make()
+            if hit is not None and hit[1].shape == new.shape:
+                hit[1].copy_(new)  # in place: a captured graph keeps reading this address
+                new = hit[1]
+        hit = (t._version, new, make)
         entry[1][tag] = hit
-    return hit[1]
+    return hit[1], fresh
+
+
+def refresh_padded_() -> int:
+    """Rebuild, in place, every padded operand whose source tensor has been modified since it was made (the captured
+    graphs of conv_in / conv_out read the padded copies, not the parameters).  Returns how many were rewritten."""
+    n = 0
+    for ref, tags in list(_PADDED.values()):
+        t = ref()
+        if t is None:
+            continue
+        for tag, (version, padded, make) in list(tags.items()):
+            if version != t._version:
+                with torch.no_grad():
+                    padded.copy_(make())
+                tags[tag] = (t._version, padded, make)
+                n += 1
+    return n
 
 
 def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
@@ -314,12 +340,13 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1, padding: int = 1,
            temb: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-           nchw_output: bool = False, block_n: int = 0) -> torch.Tensor:
+           nchw_output: bool = False, block_n: int = 0, w_static: bool = False) -> torch.Tensor:
     """Conv2d for the SDXL UNet sites: 3x3/pad 1 (stride 1 or 2) and 1x1/pad 0, channels-last.
 
     temb: (N, K) added per (image, channel) after the bias (unet_pt.py:82-83).
     residual: (N, K, H, W) added after the bias (unet_pt.py:93).  Both are fused into the GEMM epilogue.
     nchw_output: write a dense NCHW result (conv_out -> the latent the scheduler consumes).
+    w_static: as in `linear` (dropped if the weight has to be re-packed / padded by this call).
     """
     _require_bf16_cuda("conv2d", x, weight, bias, temb, residual)
     _ensure_workspace(x.device)
@@ -332,6 +359,9 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     L = lib()
     stream = _stream(x)
     wp = pack_conv_weight(weight)
+    if wp is not weight:
+        w_static = False  # packed on this stream just now (compile() pre-packs, so the hot path never gets here)
+    wflag = ST_W_STATIC if w_static else 0
     if temb is not None and temb.shape != (n, k):
         raise ValueError(f"conv2d: temb must be (N, K) = ({n}, {k}), got {tuple(temb.shape)}")
 
@@ -347,7 +377,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         if temb is not None:
             raise ValueError("conv2d: temb epilogue is only wired for 3x3 convolutions")
         check(L.st_gemm_bf16(xn.data_ptr(), c, wp.data_ptr(), c, out.data_ptr(), k, n * h * w, k, c, _ptr(bias),
-                             res_ptr, k, ST_W_STATIC, block_n, stream), "conv1x1")
+                             res_ptr, k, wflag, block_n, stream), "conv1x1")
         return out
 
     if (r, s) != (3, 3) or padding != 1:
@@ -358,15 +388,16 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             raise ValueError("conv2d: small-channel path supports plain stride-1 convolution only")
         if c <= 7:
             # conv_in: im2col to [M, 64] (9*C real columns) x weight padded to (K, 64); NCHW input consumed in place
-            wpad = _padded(weight, "smallc", lambda: torch.nn.functional.pad(
-                wp.permute(0, 2, 3, 1).reshape(k, 9 * c), (0, 64 - 9 * c)).contiguous())
+            wref = weakref.ref(weight)  # the maker re-reads the LIVE weight (refresh_padded_) without keeping it alive
+            wpad, fresh = _padded(weight, "smallc", lambda: torch.nn.functional.pad(
+                pack_conv_weight(wref()).permute(0, 2, 3, 1).reshape(k, 9 * c), (0, 64 - 9 * c)).contiguous())
             col = torch.empty((n * h * w, 64), dtype=BF16, device=x.device)
             xs = x.stride()
             check(L.st_im2col3x3_smallc_bf16(x.data_ptr(), xs[0], xs[2], xs[3], xs[1], col.data_ptr(), n, h, w, c,
                                              stream), "im2col_smallc")
             out = _empty_nhwc(n, k, h, w, x)
             check(L.st_gemm_bf16(col.data_ptr(), 64, wpad.data_ptr(), 64, out.data_ptr(), k, n * h * w, k, 64,
-                                 _ptr(bias), 0, 0, ST_W_STATIC, block_n, stream), "conv_in")
+                                 _ptr(bias), 0, 0, 0 if fresh else wflag, block_n, stream), "conv_in")
             return out
         # conv_out: pad the K <= 8 output channels to 8, implicit GEMM, then gather the real channels
         if c % 64 != 0 or (h * w) % 128 != 0 and 128 % (h * w) != 0:
@@ -378,12 +409,16 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
                   "conv_out")
             return out
         xn = _nhwc(x)
-        w8 = _padded(weight, "k8", lambda: torch.nn.functional.pad(
-            wp.permute(0, 2, 3, 1).reshape(k, 9 * c), (0, 0, 0, 8 - k)).contiguous())
-        b8 = None if bias is None else _padded(bias, "k8", lambda: torch.nn.functional.pad(bias, (0, 8 - k)).contiguous())
+        wref = weakref.ref(weight)
+        w8, fresh = _padded(weight, "k8", lambda: torch.nn.functional.pad(
+            pack_conv_weight(wref()).permute(0, 2, 3, 1).reshape(k, 9 * c), (0, 0, 0, 8 - k)).contiguous())
+        b8 = None
+        if bias is not None:
+            bref = weakref.ref(bias)
+            b8 = _padded(bias, "k8", lambda: torch.nn.functional.pad(bref(), (0, 8 - k)).contiguous())[0]
         y8 = torch.empty((n * h * w, 8), dtype=BF16, device=x.device)
-        check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), w8.data_ptr(), _ptr(b8), y8.data_ptr(), n, h, w, c, 8, 0, 0, 0, ST_W_STATIC,
-                                     64, stream), "conv_out")
+        check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), w8.data_ptr(), _ptr(b8), y8.data_ptr(), n, h, w, c, 8, 0, 0, 0,
+                                     0 if fresh else wflag, 64, stream), "conv_out")
         if not nchw_output:
             return y8.view(n, h, w, 8)[..., :k].permute(0, 3, 1, 2)
         out = torch.empty((n, k, h, w), dtype=BF16, device=x.device)
@@ -399,7 +434,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         check(L.st_im2col3x3_nhwc_bf16(xn.data_ptr(), col.data_ptr(), n, h, w, c, 2, stream), "im2col")
         out = _empty_nhwc(n, k, ho, wo, x)
         check(L.st_gemm_bf16(col.data_ptr(), 9 * c, wp.data_ptr(), 9 * c, out.data_ptr(), k, n * ho * wo, k, 9 * c,
-                             _ptr(bias), 0, 0, ST_W_STATIC, block_n, stream), "conv_s2")
+                             _ptr(bias), 0, 0, wflag, block_n, stream), "conv_s2")
         return out
     if stride != 1:
         raise ValueError("conv2d: stride must be 1 or 2")
@@ -412,7 +447,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         residual = _nhwc(residual)
         res_ptr = residual.data_ptr()
     check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), wp.data_ptr(), _ptr(bias), out.data_ptr(), n, h, w, c, k, _ptr(temb),
-                                 temb.stride(0) if temb is not None else 0, res_ptr, ST_W_STATIC, block_n, stream),
+                                 temb.stride(0) if temb is not None else 0, res_ptr, wflag, block_n, stream),
           "conv3x3")
     return out
 

@@ -16,6 +16,11 @@ Differences, all deliberate:
     working conv, SURVEY F7), with bias / SiLU / GEGLU / time-embedding / residual epilogues fused;
   * `.config` is carried over, so `pipe.unet = compile(unet)` needs no manual patch
     (cf. implementations/Diffusers/load_sdxl_pipeline.py:29-34);
+  * weights stay live, as in the reference (wrappers read them through the original submodules): the fused projection
+    buffers (QKV, cross-attention K/V, time-embedding) ARE the storage of the parameters they were built from, so
+    in-place updates (`load_state_dict`, `weight.copy_`, a LoRA merge) reach every kernel and every captured graph;
+    after an update that replaces parameter tensors, or that touches conv_in / conv_out, call
+    `model.refresh_fused_weights()`;
   * besides forward(), the returned module offers `prepare(encoder_hidden_states, added_cond_kwargs)` and
     `step_forward(sample, timesteps, *prompt_constants)`: the prompt-constant part of the graph (cross-attention K/V
     projections, text / time-ids embedding) computed once per prompt instead of once per step (pipeline.DenoiseLoop
@@ -105,6 +110,18 @@ def optimize_model(model: torch.nn.Module, cuda_graph: bool = True, *, check_dev
     replace_backend(gm, report)
     if check_device:
         pack_weights_(gm)
+    # fused projection buffers become the storage of the parameters they were built from: weights stay live
+    P.alias_fused_parameters_(gm)
+
+    def refresh_fused_weights() -> int:
+        """Re-sync every derived weight copy with the current parameters, in place (captured graphs keep working):
+        fused projection buffers whose source parameter was REPLACED (load_state_dict(assign=True), `.to()`), and the
+        zero-padded conv_in / conv_out operands.  In-place updates of Linear weights need no call: the parameters are
+        views of the fused buffers.  Returns the number of tensors rewritten."""
+        from . import kernels as K
+        return P.refresh_fused_parameters_(gm) + K.refresh_padded_()
+
+    gm.refresh_fused_weights = refresh_fused_weights
     gm.pass_report = report
     if config is not None:
         gm.config = config

@@ -14,6 +14,10 @@ weights are read live from the model.  Reference counterparts:
 New seams the reference lacks (it left Linear / Conv2d / glue to cuBLAS / cuDNN / eager):
 `linear_geglu_wrapper`, `conv2d_wrapper`, `concat_wrapper`, `timestep_wrapper`.  No wrapper casts or
 mutates parameters (the reference's fp16 "hacks", replace_layernorm.py:19-22, are not reproduced).
+
+Every wrapper here hands module *parameters* to the kernels, so it declares them static (`w_static=True`: the kernel may
+fetch the weight ahead of its programmatic dependency on the preceding launch).  The tensor-level API in kernels.py
+defaults to `w_static=False`, where a weight may be the output of the kernel launched just before.
 """
 from __future__ import annotations
 
@@ -35,17 +39,19 @@ def layer_norm_wrapper(v: torch.Tensor, layernorm: torch.nn.LayerNorm) -> torch.
 
 def linear_wrapper(v: torch.Tensor, linear: torch.nn.Linear, activation: bool,
                    residual: Optional[torch.Tensor] = None, silu_input: bool = False) -> torch.Tensor:
-    return K.linear(v, linear.weight, linear.bias, activation=activation, residual=residual, silu_input=silu_input)
+    return K.linear(v, linear.weight, linear.bias, activation=activation, residual=residual, silu_input=silu_input,
+                    w_static=True)
 
 
 def linear_wrapper_functional(v: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                               activation: bool, silu_input: bool = False) -> torch.Tensor:
-    return K.linear(v, weight, bias, activation=activation, silu_input=silu_input)
+    # only compile()'s own fusion passes emit this call, always on (fused) parameter buffers
+    return K.linear(v, weight, bias, activation=activation, silu_input=silu_input, w_static=True)
 
 
 def linear_geglu_wrapper(v: torch.Tensor, linear: torch.nn.Linear) -> torch.Tensor:
     """GEGLU projection with the gate fused into the GEMM epilogue (unet_pt.py:155-158)."""
-    return K.linear(v, linear.weight, linear.bias, geglu=True)
+    return K.linear(v, linear.weight, linear.bias, geglu=True, w_static=True)
 
 
 def geglu_wrapper(state: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
@@ -71,7 +77,7 @@ def conv2d_wrapper(v: torch.Tensor, conv: torch.nn.Conv2d, temb: Optional[torch.
     if upsample:
         v = K.upsample_nearest2x(v)
     return K.conv2d(v, conv.weight, conv.bias, stride=conv.stride[0], padding=conv.padding[0], temb=temb,
-                    residual=residual, nchw_output=conv.out_channels <= 8)
+                    residual=residual, nchw_output=conv.out_channels <= 8, w_static=True)
 
 
 def concat_wrapper(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

@@ -29,7 +29,8 @@ def layer_norm(x, weight, bias, eps):
     return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
 
 
-def linear(x, weight, bias=None, activation=False, residual=None, geglu=False, silu_input=False, block_n=0):
+def linear(x, weight, bias=None, activation=False, residual=None, geglu=False, silu_input=False, block_n=0,
+           w_static=False):
     _count("linear_geglu" if geglu else "linear")
     if silu_input:
         x = F.silu(x)
@@ -66,7 +67,8 @@ def upsample_nearest2x(x):
     return F.interpolate(x, scale_factor=2.0, mode="nearest")
 
 
-def conv2d(x, weight, bias, stride=1, padding=1, temb=None, residual=None, nchw_output=False, block_n=0):
+def conv2d(x, weight, bias, stride=1, padding=1, temb=None, residual=None, nchw_output=False, block_n=0,
+           w_static=False):
     _count("conv2d")
     y = F.conv2d(x, weight, bias, stride=stride, padding=padding)
     if temb is not None:

@@ -52,7 +52,7 @@ def test_argument_validation_returns_error_codes(built_lib):
     assert L.st_conv3x3_nhwc_bf16(16, 16, 16, 16, 1, 16, 16, 60, 64, 0, 0, 0, 0, 0, 0) == -1
     assert L.st_conv3x3_nhwc_bf16(16, 16, 16, 16, 1, 12, 12, 64, 64, 0, 0, 0, 0, 0, 0) == -1
     assert L.st_attention_bf16(16, 64, 64, 60, 16, 64, 64, 64, 16, 64, 64, 64, 16, 64, 64, 64, 1, 1, 8, 8, 0.125, 0) == -1
-    assert L.st_linear_small_m_bf16(16, 64, 16, 64, 0, 16, 64, 33, 64, 64, 0, 0, 0) == -1
+    assert L.st_linear_small_m_bf16(16, 64, 16, 64, 0, 16, 64, 33, 64, 64, 0, 0, 0, 0) == -1
 
 
 def test_python_wrappers_reject_cpu_tensors():

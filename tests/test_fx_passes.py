@@ -188,3 +188,50 @@ def test_compile_refuses_cpu_models():
     model = synth.build_unet(UNetConfig.tiny(), seed=1, device="cpu", dtype=torch.float32)
     with pytest.raises(AssertionError):
         st.compile(model)
+
+
+def test_fused_projection_weights_stay_live_after_compile():
+    """the fused QKV / cross-attention K/V / time-embedding buffers must not freeze the weights at
+    compile() time.  The parameters are views of the fused buffers, so an in-place update reaches the rewritten graph;
+    a REPLACED parameter is picked up by refresh_fused_weights()."""
+    cfg, model, gm = _compiled_tiny()
+    inp = synth.synth_inputs(2, 16, cfg, seed=5)
+    sources = gm._st_fused_sources
+    assert any(k.startswith("_st_shared_proj_") for k in sources) and any(k.startswith("_st_temb_proj_w_") for k in sources)
+    # every q/k/v, cross-attention K/V and time_emb_proj parameter aliases its rows of a fused buffer
+    n_alias = 0
+    for buffer, parts in sources.items():
+        buf = gm.get_buffer(buffer)
+        for qualname, attr, off, rows in parts:
+            p = getattr(gm.get_submodule(qualname), attr)
+            assert p.data_ptr() == buf[off:off + rows].data_ptr() and p.shape == buf[off:off + rows].shape
+            n_alias += 1
+    assert n_alias == 3 * 17 + 2 * 17 + 2 * len([m for m in gm.modules() if hasattr(m, "time_emb_proj")])
+
+    def run(g):
+        with torch.no_grad(), fake_kernels.installed():
+            return g(**inp)[0]
+
+    before = run(gm)
+    targets = [n for n, _ in model.named_parameters()
+               if n.endswith(("attn1.to_q.weight", "attn2.to_k.weight", "time_emb_proj.weight", "time_emb_proj.bias"))]
+    assert len(targets) > 20
+    with torch.no_grad():  # in-place update through the ORIGINAL model object (compile() shares its parameters)
+        for name in targets:
+            p = model.get_parameter(name)
+            p.mul_(1.25).add_(0.01)
+        ref = model(**inp)[0]
+    after = run(gm)
+    assert not torch.allclose(after, before)
+    rel, cos = parity(after, ref)
+    assert rel < 1e-5, (rel, cos)
+
+    # replacing parameter tensors breaks the aliasing until refresh_fused_weights()
+    sd = {k: v * 0.5 for k, v in model.state_dict().items()}
+    model.load_state_dict(sd, strict=True, assign=True)
+    assert gm.refresh_fused_weights() > 0
+    with torch.no_grad():
+        ref2 = model(**inp)[0]
+    rel, cos = parity(run(gm), ref2)
+    assert rel < 1e-5, (rel, cos)
+    assert gm.refresh_fused_weights() == 0  # idempotent: everything aliases again
