@@ -285,22 +285,24 @@ def run_gpu_arm(args):
     ms_total = ev0.elapsed_time(ev1)
 
     # ---- informational: same loop with the prompt-constant part computed once per prompt ------------------
-    loop_h = DenoiseLoop(compiled, prompts=prompts, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device)
-    loop_h.set_conditioning(cond, uncond)
-    loop_h.reset(inp["sample"].float())
-    loop_h.capture()
-    loop_h.reset(inp["sample"].float())
-    for _ in range(warmup):
-        loop_h.run_step()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    h0.record()
-    for _ in range(steps):
-        loop_h.run_step()
-    h1.record()
-    barrier()
-    ms_hoisted = h0.elapsed_time(h1)
-    del loop_h
+    ms_hoisted = None
+    if not args.lean:
+        loop_h = DenoiseLoop(compiled, prompts=prompts, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device)
+        loop_h.set_conditioning(cond, uncond)
+        loop_h.reset(inp["sample"].float())
+        loop_h.capture()
+        loop_h.reset(inp["sample"].float())
+        for _ in range(warmup):
+            loop_h.run_step()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        h0.record()
+        for _ in range(steps):
+            loop_h.run_step()
+        h1.record()
+        barrier()
+        ms_hoisted = h0.elapsed_time(h1)
+        del loop_h
 
     # ---- e2e arm: public API, pinned-host inputs, H2D + D2H inside the timed region ----------------
     b2 = synth.synth_inputs(2 * prompts, latent, cfg, seed=99 + rank, device="cpu", dtype=torch.bfloat16)
@@ -450,9 +452,10 @@ def run_gpu_arm(args):
 
     # ---- max over ranks -------------------------------------------------------------------------------
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_hoisted], dtype=torch.float64, device=device)
+        t = torch.tensor([ms_total, ms_e2e, ms_hoisted or 0.0], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, ms_hoisted = t.tolist()
+        ms_total, ms_e2e = t.tolist()[:2]
+        ms_hoisted = t.tolist()[2] if ms_hoisted is not None else None
 
     if rank == 0:
         peaks = load_peaks()
@@ -533,7 +536,7 @@ def run_gpu_arm(args):
             "sustained": sustained,
             "strong_scaling": strong,
             "cfg_split": cfg_split,
-            "prompt_constants_hoisted": {
+            "prompt_constants_hoisted": None if ms_hoisted is None else {
                 "ms_per_step": ms_hoisted / steps, "value": world * prompts * steps / (ms_hoisted * 1e-3), "unit": UNIT,
                 "note": "not the headline: cross-attention K/V projections + text/time-ids embedding computed once per "
                         "prompt (compiled.prepare / step_forward, SURVEY 8f rank 2) instead of inside every step"},
@@ -587,7 +590,12 @@ def main():
     ap.add_argument("--sustained-seconds", type=float, default=5.0, help="length of the informational sustained run (0: skip)")
     ap.add_argument("--prompts-total", type=int, default=8, help="strong-scaling arm: prompts split over all ranks (0: skip)")
     ap.add_argument("--no-cfg-split", action="store_true", help="skip the 2-GPU CFG-split arm")
+    ap.add_argument("--lean", action="store_true",
+                    help="headline + e2e + roofline only (batch / resolution sweeps): no hoisted, sustained, strong-scaling, "
+                         "CFG-split or CPU arms")
     args = ap.parse_args()
+    if args.lean:
+        args.sustained_seconds, args.prompts_total, args.no_cfg_split, args.no_cpu_baseline = 0.0, 0, True, True
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -433,10 +433,12 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
 
   static const int dbg = getenv("ST_GN_DEBUG") ? atoi(getenv("ST_GN_DEBUG")) : 0;  // 1: stats only, 2: apply only
   const size_t smem = (static_cast<size_t>(3) * C + static_cast<size_t>(g.pix_lanes) * 2 * C) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per context
+  const int dev = current_device();
+  ST_CHECK_ARG(dev >= 0, "groupnorm: device ordinal outside [0, %d)", kMaxDevices);
+  if (!configured.done(dev)) {
     cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    configured = true;
+    configured.mark(dev);
   }
   ST_CHECK_ARG(smem <= 96 * 1024, "groupnorm: C (%d) needs too much shared memory", C);
   static std::atomic<unsigned> next_ticket_row{0};

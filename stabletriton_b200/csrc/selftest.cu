@@ -755,6 +755,36 @@ int main(int argc, char** argv) {
     test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, true);
     return g_fail ? 1 : 0;
   }
+  if (!strcmp(what, "sanitize")) {
+    // one small, untimed case per kernel family: the compute-sanitizer targets (tools/sanitize.sh; memcheck, racecheck
+    // and synccheck multiply the run time by 10-100x, so the shapes are the smallest that exercise every pipeline:
+    // multi-tile persistent GEMM with a ragged edge, every epilogue, multi-block attention sweeps, both norm kernels)
+    const char* fam = argc > 2 ? argv[2] : "all";
+    const bool every = !strcmp(fam, "all");
+    if (every || !strcmp(fam, "gemm")) {
+      test_gemm_case(300, 328, 192, ST_W_STATIC, true, true, 192, false);
+      test_gemm_case(256, 512, 128, ST_EPI_GEGLU | ST_W_STATIC, true, false, 128, false);
+      test_gemm_case(384, 320, 320, ST_EPI_SILU, true, false, 0, false);
+      test_gemm_case(130, 72, 64, ST_EPI_SILU, true, true, 64, false);
+    }
+    if (every || !strcmp(fam, "conv")) {
+      test_conv_case(2, 16, 16, 64, 64, true, false, 0, false);
+      test_conv_case(1, 8, 8, 128, 192, false, true, 0, false);
+    }
+    if (every || !strcmp(fam, "attn")) {
+      test_attn_case(1, 2, 384, 384, true, false);   // pipelined kernel, 3 K/V blocks
+      test_attn_case(1, 2, 200, 77, false, false);   // one-block kernel, ragged Tq and Tk
+    }
+    if (every || !strcmp(fam, "norm")) {
+      test_groupnorm_case(2, 256, 320, 32, true, 0.f, false);
+      test_groupnorm_case(1, 100, 2560, 32, false, 0.f, false);
+      test_layernorm_case(77, 640, false);
+      test_layernorm_case(300, 1280, false);
+    }
+    if (every || !strcmp(fam, "misc")) test_misc();
+    printf("sanitize %s: %d failure(s), %llu kernel launches\n", fam, g_fail, st_launch_count());
+    return g_fail ? 1 : 0;
+  }
   const bool all = !strcmp(what, "all");
   if (all || !strcmp(what, "gemm")) test_gemm();
   if (all || !strcmp(what, "conv")) test_conv();
