@@ -58,10 +58,24 @@ int st_set_workspace(void* ptr, size_t bytes);
  * (reference: kernels/groupnorm.py:128-161; wrapper optimizers/replace_groupnorm.py:18-19) with
  * torch.nn.GroupNorm semantics (biased variance) on 4-D input, which the reference kernel gets
  * wrong.  x, y: [N, HW, C] bf16; gamma, beta: [C] bf16; C % groups == 0, C % 8 == 0.
- * workspace: st_groupnorm_workspace_bytes() bytes of scratch, 16-byte aligned. */
+ * workspace: st_groupnorm_workspace_bytes() bytes of scratch, 16-byte aligned, owned by THIS call (per-image arrival
+ * tickets, partial statistics, per-channel scale / shift all live there -- no library-global state, so concurrent calls
+ * on different streams or in different captured graphs never interact).  Contents on entry are irrelevant.
+ * Activations larger than 48 MB are processed in image groups so that the normalise pass finds its input in L2. */
 size_t st_groupnorm_workspace_bytes(int N, int HW, int C, int groups);
 int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, void* workspace, int N,
                            int HW, int C, int groups, float eps, int apply_silu, st_stream_t stream);
+
+/* GroupNorm whose statistics were already emitted by the producer(s) of x: st_gemm_bf16 / st_conv3x3_nhwc_bf16 called
+ * with `gn_partial` write, per 128-row tile and output column, (mean, M2) of the values they store; this entry point
+ * merges them per (image, group) and normalises -- x is read ONCE (the reference's kernel, and the stand-alone entry
+ * point above, read it twice: kernels/groupnorm.py:24-119).  Needs HW % 128 == 0.  part_a: [N*HW/128, C_a, 2] fp32;
+ * part_b (may be NULL with C_b = 0): [N*HW/128, C_b, 2] for x = concat(a, b) along channels (unet_pt.py:356,385), whose
+ * statistics are those of its two producers; C_a + C_b == C.  workspace: as above (only N*C*2 floats are used). */
+int st_groupnorm_from_partials_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, void* workspace,
+                                         int N, int HW, int C, int groups, float eps, int apply_silu,
+                                         const void* part_a, int C_a, const void* part_b, int C_b,
+                                         st_stream_t stream);
 
 /* ---- LayerNorm over the last dimension --------------------------------------------------------
  * Replaces layer_norm(x, weight, bias, eps) (reference: kernels/layer_norm.py:338-346, kernel
@@ -84,9 +98,13 @@ int st_geglu_bf16(const void* state, int ld_state, const void* gate, int ld_gate
  *   D[M, n_out] = epi(A[M, K] . W[N, K]^T + bias[N]) (+ residual[M, n_out])
  * A: activations, row pitch lda; W: nn.Linear weight layout (N rows of K), row pitch ldw; K % 64 == 0,
  * lda/ldw % 8 == 0, pointers 16-byte aligned.  With ST_EPI_GEGLU, N = 2*n_out and D has n_out columns;
- * otherwise n_out = N.  bias / residual may be NULL.  block_n: 0 = choose automatically. */
+ * otherwise n_out = N.  bias / residual may be NULL.  block_n: 0 = choose automatically.
+ * gn_partial (may be NULL): fp32 [M/128, n_out, 2]; the epilogue also writes (mean, M2) of every output column over
+ * the 128 rows of each row tile, computed from the bf16 values it stores -- the input of
+ * st_groupnorm_from_partials_nhwc_bf16.  Needs M % 128 == 0, no GEGLU. */
 int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ldd, int M, int N, int K,
-                 const void* bias, const void* residual, int ldr, unsigned flags, int block_n, st_stream_t stream);
+                 const void* bias, const void* residual, int ldr, unsigned flags, int block_n, void* gn_partial,
+                 st_stream_t stream);
 
 /* Tiny-M Linear (time / added-condition embeddings, M <= 32): y = act_out(act_in(x) . W^T + b).
  * CUDA-core, weight-bandwidth bound.  silu_in applies SiLU to x on load (unet_pt.py:81-82).  flags: ST_W_STATIC
@@ -101,10 +119,11 @@ int st_linear_small_m_bf16(const void* x, int ldx, const void* W, int ldw, const
  * x: [N, H, W, C]; w: [K, 3, 3, C] (KRSC == channels-last Conv2d weight); y: [N, H, W, K].
  * y = conv(x, w) + bias[K] (+ temb[N, K] broadcast over pixels, unet_pt.py:82-83) (+ residual[N,H,W,K],
  * unet_pt.py:93).  Needs C % 64 == 0, K % 8 == 0 and either (H*W) % 128 == 0 with W dividing 128 or a multiple of it, or
- * H*W dividing 128 (small feature maps: one tile covers several whole images). */
+ * H*W dividing 128 (small feature maps: one tile covers several whole images).
+ * gn_partial (may be NULL): fp32 [N*H*W/128, K, 2], as in st_gemm_bf16 (needs N*H*W % 128 == 0). */
 int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int C, int K,
                          const void* temb, int ld_temb, const void* residual, unsigned flags, int block_n,
-                         st_stream_t stream);
+                         void* gn_partial, st_stream_t stream);
 
 /* Small-channel direct 3x3 conv (pad 1, stride 1) for conv_in (C=4 -> 320) and conv_out (320 -> 4)
  * (unet_pt.py:430,467).  CUDA-core.  Either C <= 8 (then K % 8 == 0, y dense NHWC, x addressed through

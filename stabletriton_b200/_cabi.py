@@ -30,9 +30,10 @@ PROTOTYPES = {
     "st_groupnorm_nhwc_bf16": (I, [P, P, P, P, P, I, I, I, I, F, I, P]),
     "st_layernorm_bf16": (I, [P, I, P, I, P, P, I, I, F, P]),
     "st_geglu_bf16": (I, [P, I, P, I, P, I, I, I, P]),
-    "st_gemm_bf16": (I, [P, I, P, I, P, I, I, I, I, P, P, I, U, I, P]),
+    "st_groupnorm_from_partials_nhwc_bf16": (I, [P, P, P, P, P, I, I, I, I, F, I, P, I, P, I, P]),
+    "st_gemm_bf16": (I, [P, I, P, I, P, I, I, I, I, P, P, I, U, I, P, P]),
     "st_linear_small_m_bf16": (I, [P, I, P, I, P, P, I, I, I, I, I, I, U, P]),
-    "st_conv3x3_nhwc_bf16": (I, [P, P, P, P, I, I, I, I, I, P, I, P, U, I, P]),
+    "st_conv3x3_nhwc_bf16": (I, [P, P, P, P, I, I, I, I, I, P, I, P, U, I, P, P]),
     "st_conv3x3_direct_bf16": (I, [P, LL, LL, LL, LL, P, P, P, LL, LL, LL, LL, I, I, I, I, I, P]),
     "st_im2col3x3_nhwc_bf16": (I, [P, P, I, I, I, I, I, P]),
     "st_upsample_nearest2x_nhwc_bf16": (I, [P, P, I, I, I, I, P]),

@@ -169,7 +169,8 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 extern "C" {
 
 int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ldd, int M, int N, int K,
-                 const void* bias, const void* residual, int ldr, unsigned flags, int block_n, st_stream_t stream) {
+                 const void* bias, const void* residual, int ldr, unsigned flags, int block_n, void* gn_partial,
+                 st_stream_t stream) {
   using namespace st;
   ST_CHECK_ARG(A && W && D, "gemm: null pointer");
   ST_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: M, N, K must be positive (got %d, %d, %d)", M, N, K);
@@ -185,6 +186,8 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   ST_CHECK_ARG(!bias || aligned16(bias), "gemm: bias must be 16-byte aligned");
   ST_CHECK_ARG(!residual || (aligned16(residual) && ldr % 8 == 0 && ldr >= n_out), "gemm: bad residual pitch/alignment");
   ST_CHECK_ARG(!(geglu && (flags & ST_EPI_SILU)), "gemm: GEGLU and SiLU epilogues are exclusive");
+  ST_CHECK_ARG(!gn_partial || (!geglu && M % kGemmBlockM == 0 && aligned16(gn_partial)),
+               "gemm: GroupNorm partials need M %% 128 == 0 (got %d), no GEGLU and a 16-byte aligned buffer", M);
 
   float* sk_ws = nullptr;
   unsigned* sk_flags = nullptr;
@@ -192,7 +195,7 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   if (block_n == 0) {
     block_n = choose_block_n(M, n_out, geglu, K);
     const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-    if (!geglu && want_stream_k(mb * ((n_out + 255) / 256), K / kGemmBlockK, mb * ((n_out + block_n - 1) / block_n),
+    if (!geglu && !gn_partial && want_stream_k(mb * ((n_out + 255) / 256), K / kGemmBlockK, mb * ((n_out + block_n - 1) / block_n),
                                 &sk_ws, &sk_flags)) {
       stream_k = true;
       block_n = 256;
@@ -220,7 +223,8 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
   p.ws = sk_ws;
   p.flags = sk_flags;
-  p.cluster = (!stream_k && want_cluster(M, n_out, block_n, geglu)) ? 1 : 0;
+  p.cluster = (!stream_k && !gn_partial && want_cluster(M, n_out, block_n, geglu)) ? 1 : 0;
+  p.gn_part = static_cast<float*>(gn_partial);
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, M, K, lda, kGemmBlockM);
@@ -235,7 +239,7 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
 
 int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int C, int K,
                          const void* temb, int ld_temb, const void* residual, unsigned flags, int block_n,
-                         st_stream_t stream) {
+                         void* gn_partial, st_stream_t stream) {
   using namespace st;
   ST_CHECK_ARG(x && w && y, "conv3x3: null pointer");
   ST_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && K > 0, "conv3x3: sizes must be positive");
@@ -261,13 +265,15 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   ST_CHECK_ARG(!temb || (aligned16(temb) && ld_temb % 8 == 0), "conv3x3: bad temb pitch/alignment");
 
   const int M = N * H * W;
+  ST_CHECK_ARG(!gn_partial || (M % kGemmBlockM == 0 && aligned16(gn_partial)),
+               "conv3x3: GroupNorm partials need N*H*W %% 128 == 0 and a 16-byte aligned buffer");
   float* sk_ws = nullptr;
   unsigned* sk_flags = nullptr;
   bool stream_k = false;
   if (block_n == 0) {
     block_n = choose_block_n(M, K, false, 9 * C);
     const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-    if (want_stream_k(mb * ((K + 255) / 256), 9 * C / kGemmBlockK, mb * ((K + block_n - 1) / block_n), &sk_ws,
+    if (!gn_partial && want_stream_k(mb * ((K + 255) / 256), 9 * C / kGemmBlockK, mb * ((K + block_n - 1) / block_n), &sk_ws,
                       &sk_flags)) {
       stream_k = true;
       block_n = 256;
@@ -295,7 +301,8 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
   p.ws = sk_ws;
   p.flags = sk_flags;
-  p.cluster = (!stream_k && want_cluster(N * H * W, K, block_n, false)) ? 1 : 0;
+  p.cluster = (!stream_k && !gn_partial && want_cluster(N * H * W, K, block_n, false)) ? 1 : 0;
+  p.gn_part = static_cast<float*>(gn_partial);
   p.conv_H = H;
   p.conv_W = W;
   p.conv_C = C;

@@ -56,6 +56,10 @@ struct GemmParams {
   int cluster;   // host-side choice: launch the CTA-pair instantiation
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
+  // GroupNorm statistics of the OUTPUT, emitted by the epilogue (the consumer GroupNorm then needs no statistics pass
+  // over the tensor): gn_part[m_blk][n_out][2] = (mean, M2) of each output column over the 128 rows of tile row-block
+  // m_blk, computed from the bf16-rounded values that are stored.  Requires M % 128 == 0; plain mode only.
+  float* gn_part;
   // 4-D (conv) A addressing
   int conv_H, conv_W, conv_C;  // input == output spatial size (3x3, pad 1, stride 1)
   int conv_Wt, conv_Ht;        // tile rectangle, Wt * Ht == 128
@@ -70,8 +74,9 @@ struct GemmSmem {
   static constexpr int kOutStageBytes = kGemmBlockM * 64 * 2;  // epilogue staging tile for the TMA store
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kBiasBytes = 2 * BLOCK_N * 4;  // two accumulator stages x BLOCK_N fp32
+  static constexpr int kGnBytes = 2 * 4 * 64 * 2 * 4;  // [2 group parities][4 lane quadrants][64 columns][mean, M2]
   static constexpr int kTotal =
-      STAGES * kStageBytes + kOutStageBytes + kBarrierBytes + kBiasBytes + 1024;  // +1024: alignment slack
+      STAGES * kStageBytes + kOutStageBytes + kBarrierBytes + kBiasBytes + kGnBytes + 1024;  // +1024: alignment slack
 };
 
 __host__ __device__ constexpr int tmem_cols_for(int n) {
@@ -86,6 +91,24 @@ __device__ __forceinline__ void add_bf16x8(float (&x)[8], const uint4& u) {
     x[2 * e] += f.x;
     x[2 * e + 1] += f.y;
   }
+}
+
+// Column sums over the 32 rows a warp holds (one row per lane, 32 columns per lane): a transposing butterfly -- at
+// every step a lane keeps the half of its values whose column bit matches its lane bit and hands the other half to
+// its partner -- 31 shuffles instead of the 160 of a per-column butterfly.  On return lane l holds in v[0] the sum of
+// column l over all 32 lanes, accumulated in a fixed order (bit-reproducible).
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? v[i] : v[i + w];
+      const float keep = up ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
 }
 
 // kConvA: A through the 4-D NHWC map.  kGeglu: B tile = [BLOCK_N/2 "state" rows | BLOCK_N/2 "gate" rows].
@@ -118,6 +141,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_bias = reinterpret_cast<float*>(s_out + S::kOutStageBytes + S::kBarrierBytes);  // [2][BLOCK_N]
+  float* s_gn = s_bias + 2 * BLOCK_N;                                                      // [2][4][64][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -547,6 +571,27 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           o.w = pack_bf16x2(x[j + 6], x[j + 7]);
           const int chunk = half * 4 + (j >> 3);
           *reinterpret_cast<uint4*>(s_stage + tile_row * 128 + ((chunk ^ (tile_row & 7)) << 4)) = o;
+          if (!kGeglu && !kStreamK && !kCluster && p.gn_part) {  // keep the ROUNDED values: the statistics are those of the stored tensor
+            const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              x[j + 2 * e] = __uint_as_float(w4[e] << 16);
+              x[j + 2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u);
+            }
+          }
+        }
+        float* gn_slot = s_gn + (g & 1) * (4 * 64 * 2);
+        if (!kGeglu && !kStreamK && !kCluster && p.gn_part) {
+          // (mean, M2) of my 32 columns over this warp's 32 rows -> shared memory; merged over the 4 lane quadrants
+          // after the barrier below (no extra synchronisation: see the buffer parity)
+          float sq[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sq[e] = x[e] * x[e];
+          const float s1 = warp_column_sums(x, lane);
+          const float s2 = warp_column_sums(sq, lane);
+          const float mean = s1 * (1.f / 32.f);
+          const float m2 = fmaxf(s2 - s1 * mean, 0.f);
+          *reinterpret_cast<float2*>(gn_slot + (quad * 64 + half * 32 + lane) * 2) = make_float2(mean, m2);
         }
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(9);
         // 64 columns staged: hand them to the TMA store engine (clips rows >= M and columns >= n_out)
@@ -555,6 +600,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (etid == 0) {
           tma_store_2d(&tmap_d, s_stage, n0 + g * 64, m_blk * kGemmBlockM);
           tma_store_commit();
+        }
+        if (!kGeglu && !kStreamK && !kCluster && p.gn_part && etid >= 64 && etid < 128) {
+          // one thread per column: merge the four 32-row partials (equal counts), fixed order
+          const int col = etid - 64;
+          const int gcol = n0 + g * 64 + col;
+          if (gcol < p.n_out) {
+            float2 q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const float2*>(gn_slot + (i * 64 + col) * 2);
+            const float mean = ((q[0].x + q[1].x) + (q[2].x + q[3].x)) * 0.25f;
+            float m2 = (q[0].y + q[1].y) + (q[2].y + q[3].y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float d = q[i].x - mean;
+              m2 = fmaf(32.f * d, d, m2);
+            }
+            *reinterpret_cast<float2*>(p.gn_part + (static_cast<size_t>(m_blk) * p.n_out + gcol) * 2) =
+                make_float2(mean, m2);
+          }
         }
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(11);
       }

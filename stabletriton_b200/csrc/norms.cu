@@ -43,12 +43,14 @@ constexpr int kGnMaxThreads = 320;   // >= C/8 for C <= 2560; small CTAs so that
 constexpr int kGnMaxImages = 4096;
 constexpr int kGnStatsPixPerThread = 8;  // 8 x 16 B in flight per thread
 constexpr int kGnApplyPixPerThread = 6;
-// Per-image arrival tickets (the finalising CTA resets its own).  Launches on different streams may overlap, so each
-// launch gets its own row of tickets: the host hands out rows round-robin (kGnTicketRows launches would have to be in
-// flight at once for two of them to share one; a row index is baked into the kernel arguments, so every GroupNorm node
-// of a captured graph keeps the row it was captured with).
-constexpr int kGnTicketRows = 256;
-__device__ unsigned int g_gn_arrivals[kGnTicketRows][kGnMaxImages];
+// Per-image arrival tickets live in the CALLER's workspace (one word per image, zeroed by gn_ticket_zero_kernel at the
+// head of every call): two GroupNorm calls that run concurrently -- different streams, parallel graph branches, two
+// captured graphs replayed at once -- necessarily own different workspaces, so they can never see each other's
+// tickets (a library-global table, however it is indexed, cannot promise that), and a faulted launch leaves nothing
+// behind.
+// An activation larger than this is processed in image groups of at most this many bytes (statistics, then apply, per
+// group), so that the apply pass still finds its input in the 126 MB L2: one HBM read + one write whatever N is.
+constexpr size_t kGnL2WindowBytes = 48u << 20;
 
 struct GnGeom {
   int N, HW, C, G, cpg;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kGnMaxThreads, 3)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial,
                 const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                 float* __restrict__ scale_shift, int HW, int C, int G, int cpg, int vecs, int pix_lanes,
-                int pix_per_chunk, float eps, int ticket_row) {
+                int pix_per_chunk, float eps, unsigned int* __restrict__ tickets) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_gn[];  // [C] shift | [C] sum(x - shift) | [C] sum((x - shift)^2) | per-thread partials
@@ -197,7 +199,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   // ticket: the last CTA of image n merges all chunks
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&g_gn_arrivals[ticket_row][n], 1u) == static_cast<unsigned>(chunks - 1));
+  if (threadIdx.x == 0) s_last = (atomicAdd(&tickets[n], 1u) == static_cast<unsigned>(chunks - 1));
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -256,7 +258,65 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
       o[1] = be - mean * sc;
     }
   }
-  if (threadIdx.x == 0) g_gn_arrivals[ticket_row][n] = 0u;
+  if (threadIdx.x == 0) tickets[n] = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+gn_ticket_zero_kernel(unsigned int* __restrict__ tickets, int n) {
+  pdl_launch_dependents();
+  pdl_wait();  // the workspace may be recycled memory that the preceding kernel still reads
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) tickets[i] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm from producer-emitted partial statistics.  The GEMM / implicit-GEMM conv epilogue that WRITES the
+// activation also writes, per 128-row tile and output column, (mean, M2) of what it stored (gemm_tc.cuh: gn_part);
+// a tile lies inside one image (HW % 128 == 0), so image n owns tiles [n * HW/128, (n+1) * HW/128).  This kernel
+// merges them per (image, group) -- every partial has the same count (128), so the merge is mean = avg(mean_i),
+// M2 = sum(M2_i) + 128 * sum((mean_i - mean)^2), evaluated in a fixed order -- and writes per-channel scale / shift;
+// gn_apply_kernel then streams the activation ONCE.  A channel concatenation (up-block skip connections) never has
+// to be reduced again: channels [0, C_a) come from the first producer's partials, [C_a, C) from the second's.
+// One warp per (image, group).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float* __restrict__ part_a, int C_a, const float* __restrict__ part_b, int C_b,
+                   const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                   float* __restrict__ scale_shift, int tiles, int C, int G, int cpg, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int n = blockIdx.y;
+  if (g >= G) return;
+  const int entries = tiles * cpg;
+  auto entry = [&](int idx) -> float2 {
+    const int t = idx / cpg;
+    const int ch = g * cpg + (idx - t * cpg);
+    const size_t tile = static_cast<size_t>(n) * tiles + t;
+    const float* src = ch < C_a ? part_a + (tile * C_a + ch) * 2 : part_b + (tile * C_b + (ch - C_a)) * 2;
+    return __ldcg(reinterpret_cast<const float2*>(src));
+  };
+  float msum = 0.f;
+  for (int i = lane; i < entries; i += 32) msum += entry(i).x;
+  msum = warp_sum(msum);
+  const float mean = msum / static_cast<float>(entries);
+  float m2 = 0.f;
+  for (int i = lane; i < entries; i += 32) {
+    const float2 e = entry(i);
+    const float d = e.x - mean;
+    m2 += fmaf(128.f * d, d, e.y);
+  }
+  m2 = warp_sum(m2);
+  const float rstd = rsqrtf(m2 / (128.f * static_cast<float>(entries)) + eps);  // biased variance, as torch.nn.GroupNorm
+  for (int c = lane; c < cpg; c += 32) {
+    const int ch = g * cpg + c;
+    const float ga = gamma ? __bfloat162float(gamma[ch]) : 1.f;
+    const float be = beta ? __bfloat162float(beta[ch]) : 0.f;
+    const float sc = ga * rstd;
+    float* o = scale_shift + (static_cast<size_t>(n) * C + ch) * 2;
+    o[0] = sc;
+    o[1] = be - mean * sc;
+  }
 }
 
 // Pass 3: y = silu?(x * scale + shift), streaming.
@@ -405,16 +465,26 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 extern "C" {
 
-size_t st_groupnorm_workspace_bytes(int N, int HW, int C, int groups) {
-  if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0 || C % 8 != 0) return 0;
-  const st::GnGeom g = st::gn_geometry(N, HW, C, groups);
-  const size_t partial = static_cast<size_t>(N) * g.chunks * groups * 3;
-  const size_t ss = static_cast<size_t>(N) * C * 2;
-  return ((partial + 3) / 4 * 4 + ss) * sizeof(float);
+// workspace layout: [tickets: N words, padded to 16 B] [partial: per image group] [scale_shift: N * C * 2 floats]
+static size_t gn_ticket_floats(int N) { return (static_cast<size_t>(N) + 3) / 4 * 4; }
+
+static int gn_images_per_round(int N, int HW, int C) {
+  const size_t per_image = static_cast<size_t>(HW) * C * 2;
+  size_t n = st::kGnL2WindowBytes / (per_image ? per_image : 1);
+  if (n < 1) n = 1;
+  return n < static_cast<size_t>(N) ? static_cast<int>(n) : N;
 }
 
-int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, void* workspace, int N,
-                           int HW, int C, int groups, float eps, int apply_silu, st_stream_t stream) {
+size_t st_groupnorm_workspace_bytes(int N, int HW, int C, int groups) {
+  if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0 || C % 8 != 0) return 0;
+  const int per_round = gn_images_per_round(N, HW, C);
+  const st::GnGeom g = st::gn_geometry(per_round, HW, C, groups);
+  const size_t partial = (static_cast<size_t>(N) * g.chunks * groups * 3 + 3) / 4 * 4;
+  const size_t ss = static_cast<size_t>(N) * C * 2;
+  return (gn_ticket_floats(N) + partial + ss) * sizeof(float);
+}
+
+static int gn_check_common(const void* x, const void* y, const void* workspace, int N, int HW, int C, int groups) {
   using namespace st;
   ST_CHECK_ARG(x && y && workspace, "groupnorm: null pointer");
   ST_CHECK_ARG(N > 0 && HW > 0 && C > 0 && groups > 0, "groupnorm: sizes must be positive");
@@ -422,16 +492,39 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
   ST_CHECK_ARG(C % groups == 0, "groupnorm: C (%d) not divisible by groups (%d)", C, groups);
   ST_CHECK_ARG(C % 8 == 0, "groupnorm: C (%d) must be a multiple of 8", C);
   ST_CHECK_ARG(C / 8 <= kGnMaxThreads, "groupnorm: C (%d) too large (max %d)", C, 8 * kGnMaxThreads);
+  ST_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(workspace), "groupnorm: pointers must be 16-byte aligned");
+  return ST_OK;
+}
+
+static int gn_launch_apply(const void* x, void* y, const float* scale_shift, int n_images, int HW, int C,
+                           const st::GnGeom& g, int apply_silu, cudaStream_t s) {
+  using namespace st;
+  const dim3 agrid(g.a_chunks, n_images);
+  if (apply_silu)
+    launch_kernel(gn_apply_kernel<true>, agrid, dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
+                  static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs, g.pix_lanes, g.a_pix_per_chunk);
+  else
+    launch_kernel(gn_apply_kernel<false>, agrid, dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
+                  static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs, g.pix_lanes, g.a_pix_per_chunk);
+  ST_CHECK_LAUNCH("gn_apply_kernel");
+  return ST_OK;
+}
+
+int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, void* workspace, int N,
+                           int HW, int C, int groups, float eps, int apply_silu, st_stream_t stream) {
+  using namespace st;
+  int rc = gn_check_common(x, y, workspace, N, HW, C, groups);
+  if (rc != ST_OK) return rc;
   ST_CHECK_ARG(C / groups >= 7 || C / groups == 4,
                "groupnorm: %d channels per group unsupported (a 16-byte vector may span at most two groups)", C / groups);
-  ST_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(workspace), "groupnorm: pointers must be 16-byte aligned");
-  const GnGeom g = gn_geometry(N, HW, C, groups);
+  const int per_round = gn_images_per_round(N, HW, C);
+  const GnGeom g = gn_geometry(per_round, HW, C, groups);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  float* partial = static_cast<float*>(workspace);
+  unsigned int* tickets = static_cast<unsigned int*>(workspace);
+  float* partial = static_cast<float*>(workspace) + gn_ticket_floats(N);
   const size_t partial_elems = (static_cast<size_t>(N) * g.chunks * groups * 3 + 3) / 4 * 4;
   float* scale_shift = partial + partial_elems;
 
-  static const int dbg = getenv("ST_GN_DEBUG") ? atoi(getenv("ST_GN_DEBUG")) : 0;  // 1: stats only, 2: apply only
   const size_t smem = (static_cast<size_t>(3) * C + static_cast<size_t>(g.pix_lanes) * 2 * C) * sizeof(float);
   static PerDeviceOnce configured;  // function attributes are per context
   const int dev = current_device();
@@ -441,23 +534,44 @@ int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void
     configured.mark(dev);
   }
   ST_CHECK_ARG(smem <= 96 * 1024, "groupnorm: C (%d) needs too much shared memory", C);
-  static std::atomic<unsigned> next_ticket_row{0};
-  const int ticket_row = static_cast<int>(next_ticket_row.fetch_add(1, std::memory_order_relaxed) % kGnTicketRows);
-  if (dbg != 2)
-  launch_kernel(gn_stats_kernel, dim3(g.chunks, N), dim3(g.threads), smem, s, static_cast<const __nv_bfloat16*>(x),
-                partial, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), scale_shift,
-                HW, C, groups, g.cpg, g.vecs, g.pix_lanes, g.pix_per_chunk, eps, ticket_row);
-  ST_CHECK_LAUNCH("gn_stats_kernel");
-  const dim3 agrid(g.a_chunks, N);
-  if (dbg == 1) return ST_OK;
-  if (apply_silu)
-    launch_kernel(gn_apply_kernel<true>, agrid, dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
-                  static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs, g.pix_lanes, g.a_pix_per_chunk);
-  else
-    launch_kernel(gn_apply_kernel<false>, agrid, dim3(g.threads), 0, s, static_cast<const __nv_bfloat16*>(x),
-                  static_cast<__nv_bfloat16*>(y), scale_shift, HW, C, g.vecs, g.pix_lanes, g.a_pix_per_chunk);
-  ST_CHECK_LAUNCH("gn_apply_kernel");
+  launch_kernel(gn_ticket_zero_kernel, dim3((N + 255) / 256), dim3(256), 0, s, tickets, N);
+  ST_CHECK_LAUNCH("gn_ticket_zero_kernel");
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  for (int n0 = 0; n0 < N; n0 += per_round) {  // one round unless the activation exceeds the L2 window
+    const int nr = N - n0 < per_round ? N - n0 : per_round;
+    const size_t off = static_cast<size_t>(n0) * HW * C;
+    launch_kernel(gn_stats_kernel, dim3(g.chunks, nr), dim3(g.threads), smem, s, xp + off,
+                  partial + static_cast<size_t>(n0) * g.chunks * groups * 3, static_cast<const __nv_bfloat16*>(gamma),
+                  static_cast<const __nv_bfloat16*>(beta), scale_shift + static_cast<size_t>(n0) * C * 2, HW, C, groups,
+                  g.cpg, g.vecs, g.pix_lanes, g.pix_per_chunk, eps, tickets + n0);
+    ST_CHECK_LAUNCH("gn_stats_kernel");
+    rc = gn_launch_apply(xp + off, yp + off, scale_shift + static_cast<size_t>(n0) * C * 2, nr, HW, C, g, apply_silu, s);
+    if (rc != ST_OK) return rc;
+  }
   return ST_OK;
+}
+
+int st_groupnorm_from_partials_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, void* workspace,
+                                         int N, int HW, int C, int groups, float eps, int apply_silu,
+                                         const void* part_a, int C_a, const void* part_b, int C_b,
+                                         st_stream_t stream) {
+  using namespace st;
+  int rc = gn_check_common(x, y, workspace, N, HW, C, groups);
+  if (rc != ST_OK) return rc;
+  ST_CHECK_ARG(HW % 128 == 0, "groupnorm_from_partials: H*W (%d) must be a multiple of the 128-row producer tile", HW);
+  ST_CHECK_ARG(part_a && C_a > 0 && C_b >= 0 && C_a + C_b == C && (C_b == 0 || part_b),
+               "groupnorm_from_partials: channel split %d + %d does not match C = %d", C_a, C_b, C);
+  ST_CHECK_ARG(aligned16(part_a) && (!part_b || aligned16(part_b)) && C_a % 2 == 0,
+               "groupnorm_from_partials: partial buffers must be 16-byte aligned");
+  const GnGeom g = gn_geometry(N, HW, C, groups);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* scale_shift = static_cast<float*>(workspace);  // N * C * 2 floats (st_groupnorm_workspace_bytes covers it)
+  launch_kernel(gn_finalize_kernel, dim3((groups + 3) / 4, N), dim3(128), 0, s, static_cast<const float*>(part_a), C_a,
+                static_cast<const float*>(part_b), C_b, static_cast<const __nv_bfloat16*>(gamma),
+                static_cast<const __nv_bfloat16*>(beta), scale_shift, HW / 128, C, groups, g.cpg, eps);
+  ST_CHECK_LAUNCH("gn_finalize_kernel");
+  return gn_launch_apply(x, y, scale_shift, N, HW, C, g, apply_silu, s);
 }
 
 int st_layernorm_bf16(const void* x, int ldx, void* y, int ldy, const void* gamma, const void* beta, int M, int N,

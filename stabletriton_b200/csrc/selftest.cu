@@ -215,12 +215,12 @@ static void test_gemm_case(int M, int N, int K, unsigned flags, bool bias, bool 
   CK(cudaMalloc(&D, (size_t)M * n_out * 2));
   CK(cudaMemset(D, 0xff, (size_t)M * n_out * 2));
   CK(cudaMalloc(&Dref, (size_t)M * n_out * 4));
-  ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, block_n, 0));
+  ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, block_n, nullptr, 0));
   CK(cudaDeviceSynchronize());
   ref_gemm<<<dim3((n_out + 127) / 128, M), 128>>>(A, K, W, K, Dref, M, N, K, b, r, n_out, flags);
   CK(cudaDeviceSynchronize());
   float ms = -1;
-  if (timeit) ms = time_ms([&](cudaStream_t s) { st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, block_n, s); });
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, block_n, nullptr, s); });
   char name[128];
   snprintf(name, sizeof name, "gemm M=%d N=%d K=%d flags=%u bias=%d res=%d bn=%d", M, N, K, flags, bias, res, block_n);
   report(name, to_host(D, (size_t)M * n_out), to_host_f(Dref, (size_t)M * n_out), 1e-2f, ms, 2.0 * M * N * K * 1e-12,
@@ -282,12 +282,12 @@ static void test_conv_case(int N, int H, int W, int C, int K, bool temb, bool re
   CK(cudaMalloc(&y, out * 2));
   CK(cudaMemset(y, 0xff, out * 2));
   CK(cudaMalloc(&yref, out * 4));
-  ST(st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, ST_W_STATIC, block_n, 0));
+  ST(st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, ST_W_STATIC, block_n, nullptr, 0));
   CK(cudaDeviceSynchronize());
   ref_conv3x3<<<dim3((K + 127) / 128, N * H * W), 128>>>(x, w, b, yref, N, H, W, C, K, t, r);
   CK(cudaDeviceSynchronize());
   float ms = -1;
-  if (timeit) ms = time_ms([&](cudaStream_t s) { st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, ST_W_STATIC, block_n, s); });
+  if (timeit) ms = time_ms([&](cudaStream_t s) { st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, r, ST_W_STATIC, block_n, nullptr, s); });
   char name[128];
   snprintf(name, sizeof name, "conv3x3 N=%d H=%d W=%d C=%d K=%d temb=%d res=%d bn=%d", N, H, W, C, K, temb, res,
            block_n);
@@ -579,7 +579,7 @@ static void test_misc() {
     CK(cudaMalloc(&col, (size_t)N * Ho * Wo * 9 * C * 2));
     CK(cudaMalloc(&y, (size_t)N * Ho * Wo * K * 2));
     ST(st_im2col3x3_nhwc_bf16(x, col, N, H, W, C, 2, 0));
-    ST(st_gemm_bf16(col, 9 * C, w, 9 * C, y, K, N * Ho * Wo, K, 9 * C, nullptr, nullptr, 0, 0, 0, 0));
+    ST(st_gemm_bf16(col, 9 * C, w, 9 * C, y, K, N * Ho * Wo, K, 9 * C, nullptr, nullptr, 0, 0, 0, nullptr, 0));
     CK(cudaDeviceSynchronize());
     std::vector<float> ref((size_t)N * Ho * Wo * K);
     for (int n = 0; n < N; ++n)
@@ -689,10 +689,10 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&D, (size_t)M * n_out * 2));
     unsigned long long* tr;
     CK(cudaMalloc(&tr, 148 * 12 * 8));
-    for (int it = 0; it < 3; ++it) ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, bn, 0));
+    for (int it = 0; it < 3; ++it) ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, bn, nullptr, 0));
     CK(cudaMemset(tr, 0, 148 * 12 * 8));
     st_debug_set_gemm_trace(tr);
-    ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, bn, 0));
+    ST(st_gemm_bf16(A, K, W, K, D, n_out, M, N, K, b, r, n_out, flags, bn, nullptr, 0));
     CK(cudaDeviceSynchronize());
     st_debug_set_gemm_trace(nullptr);
     std::vector<unsigned long long> h(148 * 12);

@@ -616,6 +616,61 @@ def replace_cat(gm: fx.GraphModule) -> int:
     return n
 
 
+def fuse_group_norm_statistics(gm: fx.GraphModule) -> int:
+    """GroupNorm statistics come from the producer's epilogue.  Every GroupNorm of the UNet reads a tensor written by
+    a conv / GEMM launch (resnet conv1 + temb -> norm2; resnet conv2 + shortcut, a transformer's proj_out + residual,
+    conv_in, a down- / up-sampler -> the next norm1 / transformer norm / conv_norm_out) or the channel concatenation of
+    two such tensors (up blocks, unet_pt.py:356,385).  Those producers become `*_stats_wrapper` calls that return
+    `(y, partials)`, and the GroupNorm receives the partials: it no longer makes a statistics pass over the activation
+    (46 launches and one full read of every normalised tensor per step).  Runs after every other pass."""
+    stats_of: Dict[Node, Node] = {}  # tensor node (the value other nodes consume) -> its partials node
+
+    def producer_stats(t: Node) -> Optional[Node]:
+        if t in stats_of:
+            return stats_of[t]
+        if _is_function(t, operator.getitem) and t.args[1] == 0 \
+                and _is_function(t.args[0], W.conv2d_stats_wrapper, W.linear_stats_wrapper):
+            for u in t.args[0].users:  # a producer converted for an earlier GroupNorm (skip connections are read twice)
+                if _is_function(u, operator.getitem) and u.args[1] == 1:
+                    return u
+        # y = linear_wrapper(...).reshape(b, h, w, c).permute(0, 3, 1, 2): the transformer tail (fuse_proj_out_residual)
+        lin, chain = t, []
+        if _is_method(t, "permute") and tuple(t.args[1:]) == (0, 3, 1, 2) and _is_method(t.args[0], "reshape", "view") \
+                and len(t.args[0].args) == 5 and len(t.args[0].users) == 1:
+            lin, chain = t.args[0].args[0], [t.args[0]]
+        if _is_function(lin, W.conv2d_wrapper) and lin is t:
+            target, extra = W.conv2d_stats_wrapper, {}
+        elif _is_function(lin, W.linear_wrapper) and chain and not lin.kwargs.get("silu_input", False) \
+                and len(lin.users) == 1:
+            target, extra = W.linear_stats_wrapper, {}
+        else:
+            return None
+        with gm.graph.inserting_before(lin):
+            both = gm.graph.call_function(target, lin.args, {**lin.kwargs, **extra})
+            y = gm.graph.call_function(operator.getitem, (both, 0))
+            part = gm.graph.call_function(operator.getitem, (both, 1))
+        lin.replace_all_uses_with(y)
+        gm.graph.erase_node(lin)
+        stats_of[t] = part
+        return part
+
+    n = 0
+    for gn in list(gm.graph.nodes):
+        if not _is_function(gn, W.group_norm_wrapper) or "partials" in gn.kwargs or len(gn.args) > 3:
+            continue
+        src = gn.args[0]
+        sources = list(src.args[:2]) if _is_function(src, W.concat_wrapper) else [src]
+        if not all(isinstance(x, Node) for x in sources):
+            continue
+        parts = [producer_stats(x) for x in sources]
+        if any(p is None for p in parts):
+            continue
+        gn.kwargs = {**gn.kwargs, "partials": tuple(parts)}
+        n += 1
+    _finish(gm)
+    return n
+
+
 def replace_timesteps(gm: fx.GraphModule) -> int:
     """Timesteps(t)  ==>  timestep_wrapper(t, num_channels).  (The reference's `fuse_timesteps` pattern
     matches nothing on its own model; here the module is kept a leaf while tracing.)"""

@@ -111,9 +111,20 @@ def _rows(x: torch.Tensor) -> tuple[torch.Tensor, int, int]:
 # ------------------------------------------------------------------------------------------------
 # GroupNorm (+SiLU)
 # ------------------------------------------------------------------------------------------------
+def gn_partial_rows(rows: int, rows_per_image: int) -> int:
+    """Number of 128-row tiles of a producer whose output has `rows` rows (`rows_per_image` per image), or 0 if the
+    producer cannot emit GroupNorm partials for it (a tile must lie inside one image)."""
+    return rows // 128 if (rows % 128 == 0 and rows_per_image % 128 == 0) else 0
+
+
 def groupnorm_wrapper(input: torch.Tensor, num_groups: int, weight: Optional[torch.Tensor],
-                      bias: Optional[torch.Tensor], eps: float, activation: bool = False) -> torch.Tensor:
-    """torch.nn.GroupNorm(num_groups, C, eps) [+ SiLU] on a 4-D tensor (reference: groupnorm.py:128)."""
+                      bias: Optional[torch.Tensor], eps: float, activation: bool = False,
+                      partials: Optional[tuple] = None) -> torch.Tensor:
+    """torch.nn.GroupNorm(num_groups, C, eps) [+ SiLU] on a 4-D tensor (reference: groupnorm.py:128).
+
+    partials: (part_a,) or (part_a, part_b) -- the per-tile column statistics emitted by the producer(s) of `input`
+    (`linear(..., gn_stats=True)` / `conv2d(..., gn_stats=True)`; two of them when `input` is a channel concatenation).
+    With them the activation is read once; without them a statistics pass runs first."""
     _require_bf16_cuda("groupnorm_wrapper", input, weight, bias)
     x = _nhwc(input)
     n, c, h, w = x.shape
@@ -125,6 +136,22 @@ def groupnorm_wrapper(input: torch.Tensor, num_groups: int, weight: Optional[tor
     if ws_bytes == 0:
         raise ValueError(f"groupnorm_wrapper: unsupported shape N={n} C={c} HW={h * w} groups={num_groups}")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    if partials is not None and all(p is not None for p in partials):
+        tiles = gn_partial_rows(n * h * w, h * w)
+        pa = partials[0]
+        pb = partials[1] if len(partials) > 1 else None
+        ca = pa.shape[1]
+        cb = pb.shape[1] if pb is not None else 0
+        for t in (pa, pb):
+            if t is not None and (t.dtype != torch.float32 or t.dim() != 3 or t.shape[0] != tiles or t.shape[2] != 2
+                                  or not t.is_contiguous() or t.device != x.device):
+                raise ValueError(f"groupnorm_wrapper: partial statistics must be contiguous fp32 [{tiles}, C, 2]")
+        if tiles == 0 or ca + cb != c:
+            raise ValueError(f"groupnorm_wrapper: partials cover {ca}+{cb} channels / {tiles} tiles, input has C={c}")
+        check(L.st_groupnorm_from_partials_nhwc_bf16(
+            x.data_ptr(), out.data_ptr(), _ptr(weight), _ptr(bias), ws.data_ptr(), n, h * w, c, num_groups, float(eps),
+            int(bool(activation)), pa.data_ptr(), ca, _ptr(pb), cb, _stream(x)), "groupnorm_from_partials")
+        return out
     check(L.st_groupnorm_nhwc_bf16(x.data_ptr(), out.data_ptr(), _ptr(weight), _ptr(bias), ws.data_ptr(), n, h * w, c,
                                    num_groups, float(eps), int(bool(activation)), _stream(x)), "groupnorm")
     return out
@@ -154,8 +181,11 @@ SMALL_M = 32
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, activation: bool = False,
            residual: Optional[torch.Tensor] = None, geglu: bool = False, silu_input: bool = False,
-           block_n: int = 0, w_static: bool = False) -> torch.Tensor:
+           block_n: int = 0, w_static: bool = False, gn_stats: int = 0):
     """y = epi(x @ weight.T + bias) [+ residual]; weight is (N, K) as in nn.Linear.
+
+    gn_stats = rows per image (> 0): y feeds a GroupNorm -- also return the per-tile column statistics the GEMM epilogue
+    can emit for free, as `(y, partials)`; partials is None when the shape does not allow it (see gn_partial_rows).
 
     activation: SiLU epilogue.  geglu: weight rows are [state ; gate], y = state * gelu(gate) with N/2
     columns.  residual (same shape as y) is added in fp32 before the single bf16 rounding.
@@ -183,7 +213,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         check(L.st_linear_small_m_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias),
                                        out.data_ptr(), n_out, m, n_rows, k, int(silu_input), int(activation), wflag,
                                        _stream(x)), "linear_small_m")
-        return out
+        return (out, None) if gn_stats else out
     if silu_input:
         raise ValueError("linear: silu_input is only supported on the tiny-M path (M <= 16)")
     res_ptr, ldr = 0, 0
@@ -194,9 +224,12 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         res_ptr = rr.data_ptr()
         residual = rr  # keep alive
     flags = (ST_EPI_SILU if activation else 0) | (ST_EPI_GEGLU if geglu else 0) | wflag
+    part = None
+    if gn_stats and not geglu and gn_partial_rows(m, gn_stats):
+        part = torch.empty((m // 128, n_out, 2), dtype=torch.float32, device=x.device)
     check(L.st_gemm_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), out.data_ptr(), n_out, m, n_rows, k,
-                         _ptr(bias), res_ptr, ldr, flags, block_n, _stream(x)), "gemm")
-    return out
+                         _ptr(bias), res_ptr, ldr, flags, block_n, _ptr(part), _stream(x)), "gemm")
+    return (out, part) if gn_stats else out
 
 
 def sdxl_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], activation: bool) -> torch.Tensor:
@@ -340,13 +373,20 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1, padding: int = 1,
            temb: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-           nchw_output: bool = False, block_n: int = 0, w_static: bool = False) -> torch.Tensor:
+           nchw_output: bool = False, block_n: int = 0, w_static: bool = False, gn_stats: bool = False):
+    out, part = _conv2d_impl(x, weight, bias, stride, padding, temb, residual, nchw_output, block_n, w_static, gn_stats)
+    return (out, part) if gn_stats else out
+
+
+def _conv2d_impl(x, weight, bias, stride, padding, temb, residual, nchw_output, block_n, w_static, gn_stats):
     """Conv2d for the SDXL UNet sites: 3x3/pad 1 (stride 1 or 2) and 1x1/pad 0, channels-last.
 
     temb: (N, K) added per (image, channel) after the bias (unet_pt.py:82-83).
     residual: (N, K, H, W) added after the bias (unet_pt.py:93).  Both are fused into the GEMM epilogue.
     nchw_output: write a dense NCHW result (conv_out -> the latent the scheduler consumes).
     w_static: as in `linear` (dropped if the weight has to be re-packed / padded by this call).
+    gn_stats: the result feeds a GroupNorm -- return `(y, partials)` with the per-tile column statistics emitted by the
+    GEMM epilogue (None where a path / shape cannot produce them; the GroupNorm then runs its own statistics pass).
     """
     _require_bf16_cuda("conv2d", x, weight, bias, temb, residual)
     _ensure_workspace(x.device)
@@ -358,6 +398,12 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         raise ValueError(f"conv2d: input has {cx} channels, weight expects {c}")
     L = lib()
     stream = _stream(x)
+
+    def mkpart(rows: int, rows_per_image: int):
+        if gn_stats and gn_partial_rows(rows, rows_per_image):
+            return torch.empty((rows // 128, k, 2), dtype=torch.float32, device=x.device)
+        return None
+
     wp = pack_conv_weight(weight)
     if wp is not weight:
         w_static = False  # packed on this stream just now (compile() pre-packs, so the hot path never gets here)
@@ -376,9 +422,10 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             res_ptr = residual.data_ptr()
         if temb is not None:
             raise ValueError("conv2d: temb epilogue is only wired for 3x3 convolutions")
+        part = mkpart(n * h * w, h * w)
         check(L.st_gemm_bf16(xn.data_ptr(), c, wp.data_ptr(), c, out.data_ptr(), k, n * h * w, k, c, _ptr(bias),
-                             res_ptr, k, wflag, block_n, stream), "conv1x1")
-        return out
+                             res_ptr, k, wflag, block_n, _ptr(part), stream), "conv1x1")
+        return out, part
 
     if (r, s) != (3, 3) or padding != 1:
         raise ValueError(f"conv2d: unsupported kernel {r}x{s} / padding {padding}")
@@ -396,9 +443,10 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             check(L.st_im2col3x3_smallc_bf16(x.data_ptr(), xs[0], xs[2], xs[3], xs[1], col.data_ptr(), n, h, w, c,
                                              stream), "im2col_smallc")
             out = _empty_nhwc(n, k, h, w, x)
+            part = mkpart(n * h * w, h * w)
             check(L.st_gemm_bf16(col.data_ptr(), 64, wpad.data_ptr(), 64, out.data_ptr(), k, n * h * w, k, 64,
-                                 _ptr(bias), 0, 0, 0 if fresh else wflag, block_n, stream), "conv_in")
-            return out
+                                 _ptr(bias), 0, 0, 0 if fresh else wflag, block_n, _ptr(part), stream), "conv_in")
+            return out, part
         # conv_out: pad the K <= 8 output channels to 8, implicit GEMM, then gather the real channels
         if c % 64 != 0 or (h * w) % 128 != 0 and 128 % (h * w) != 0:
             xn = _nhwc(x)  # shapes the tensor-core conv cannot tile: CUDA-core direct kernel
@@ -407,7 +455,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             check(L.st_conv3x3_direct_bf16(xn.data_ptr(), h * w * c, w * c, c, 1, wp.data_ptr(), _ptr(bias),
                                            out.data_ptr(), os_[0], os_[2], os_[3], os_[1], n, h, w, c, k, stream),
                   "conv_out")
-            return out
+            return out, None
         xn = _nhwc(x)
         wref = weakref.ref(weight)
         w8, fresh = _padded(weight, "k8", lambda: torch.nn.functional.pad(
@@ -418,12 +466,12 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             b8 = _padded(bias, "k8", lambda: torch.nn.functional.pad(bref(), (0, 8 - k)).contiguous())[0]
         y8 = torch.empty((n * h * w, 8), dtype=BF16, device=x.device)
         check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), w8.data_ptr(), _ptr(b8), y8.data_ptr(), n, h, w, c, 8, 0, 0, 0,
-                                     0 if fresh else wflag, 64, stream), "conv_out")
+                                     0 if fresh else wflag, 64, 0, stream), "conv_out")
         if not nchw_output:
-            return y8.view(n, h, w, 8)[..., :k].permute(0, 3, 1, 2)
+            return y8.view(n, h, w, 8)[..., :k].permute(0, 3, 1, 2), None
         out = torch.empty((n, k, h, w), dtype=BF16, device=x.device)
         check(L.st_nhwc_to_nchw_bf16(y8.data_ptr(), 8, out.data_ptr(), n, h * w, k, stream), "nhwc_to_nchw")
-        return out
+        return out, None
 
     xn = _nhwc(x)
     if stride == 2:
@@ -433,9 +481,10 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         col = torch.empty((n * ho * wo, 9 * c), dtype=BF16, device=x.device)
         check(L.st_im2col3x3_nhwc_bf16(xn.data_ptr(), col.data_ptr(), n, h, w, c, 2, stream), "im2col")
         out = _empty_nhwc(n, k, ho, wo, x)
+        part = mkpart(n * ho * wo, ho * wo)
         check(L.st_gemm_bf16(col.data_ptr(), 9 * c, wp.data_ptr(), 9 * c, out.data_ptr(), k, n * ho * wo, k, 9 * c,
-                             _ptr(bias), 0, 0, wflag, block_n, stream), "conv_s2")
-        return out
+                             _ptr(bias), 0, 0, wflag, block_n, _ptr(part), stream), "conv_s2")
+        return out, part
     if stride != 1:
         raise ValueError("conv2d: stride must be 1 or 2")
 
@@ -446,10 +495,11 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
             raise ValueError("conv2d: residual shape mismatch")
         residual = _nhwc(residual)
         res_ptr = residual.data_ptr()
+    part = mkpart(n * h * w, h * w)
     check(L.st_conv3x3_nhwc_bf16(xn.data_ptr(), wp.data_ptr(), _ptr(bias), out.data_ptr(), n, h, w, c, k, _ptr(temb),
-                                 temb.stride(0) if temb is not None else 0, res_ptr, wflag, block_n, stream),
+                                 temb.stride(0) if temb is not None else 0, res_ptr, wflag, block_n, _ptr(part), stream),
           "conv3x3")
-    return out
+    return out, part
 
 
 def implicit_gemm_fprop(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

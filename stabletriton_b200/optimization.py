@@ -60,6 +60,7 @@ def replace_backend(gm: fx.GraphModule, report: Dict[str, int] | None = None) ->
         ("replace_cat", P.replace_cat),
         ("replace_timesteps", P.replace_timesteps),
         ("keep_channels_last", P.keep_channels_last),
+        ("fuse_group_norm_statistics", P.fuse_group_norm_statistics),
     ]
     for name, fn in passes:
         count = fn(gm)

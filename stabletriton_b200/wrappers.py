@@ -29,8 +29,13 @@ import torch.fx
 from . import kernels as K
 
 
-def group_norm_wrapper(v: torch.Tensor, groupnorm: torch.nn.GroupNorm, activation: bool) -> torch.Tensor:
-    return K.groupnorm_wrapper(v, groupnorm.num_groups, groupnorm.weight, groupnorm.bias, groupnorm.eps, activation)
+def group_norm_wrapper(v: torch.Tensor, groupnorm: torch.nn.GroupNorm, activation: bool,
+                       partials: Optional[tuple] = None) -> torch.Tensor:
+    """partials (new): the statistics the producer(s) of `v` emitted from their GEMM epilogues -- `(part,)`, or
+    `(part_a, part_b)` when v = cat([a, b], 1) -- see linear_stats_wrapper / conv2d_stats_wrapper.  Any entry may be
+    None (producer shape not eligible): the kernel then runs its own statistics pass, as without the argument."""
+    return K.groupnorm_wrapper(v, groupnorm.num_groups, groupnorm.weight, groupnorm.bias, groupnorm.eps, activation,
+                               partials=partials)
 
 
 def layer_norm_wrapper(v: torch.Tensor, layernorm: torch.nn.LayerNorm) -> torch.Tensor:
@@ -41,6 +46,15 @@ def linear_wrapper(v: torch.Tensor, linear: torch.nn.Linear, activation: bool,
                    residual: Optional[torch.Tensor] = None, silu_input: bool = False) -> torch.Tensor:
     return K.linear(v, linear.weight, linear.bias, activation=activation, residual=residual, silu_input=silu_input,
                     w_static=True)
+
+
+def linear_stats_wrapper(v: torch.Tensor, linear: torch.nn.Linear, activation: bool,
+                         residual: Optional[torch.Tensor] = None, rows_per_image: int = 0):
+    """linear_wrapper for a result that feeds a GroupNorm (the transformer's proj_out + image residual,
+    unet_pt.py:236-243 -> the next resnet's norm1): returns (y, partials).  rows_per_image = H*W of the feature map the
+    token rows belong to; 0 = take it from v (B, H*W, C)."""
+    return K.linear(v, linear.weight, linear.bias, activation=activation, residual=residual, w_static=True,
+                    gn_stats=rows_per_image or (v.shape[-2] if v.dim() >= 3 else v.shape[0]))
 
 
 def linear_wrapper_functional(v: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
@@ -80,6 +94,20 @@ def conv2d_wrapper(v: torch.Tensor, conv: torch.nn.Conv2d, temb: Optional[torch.
                     residual=residual, nchw_output=conv.out_channels <= 8, w_static=True)
 
 
+def conv2d_stats_wrapper(v: torch.Tensor, conv: torch.nn.Conv2d, temb: Optional[torch.Tensor] = None,
+                         residual: Optional[torch.Tensor] = None, upsample: bool = False):
+    """conv2d_wrapper for a result that feeds a GroupNorm: returns (y, partials) -- the implicit-GEMM epilogue also
+    writes per-tile column statistics of what it stores, so the GroupNorm needs no statistics pass (reference: the
+    GroupNorm kernel re-reads the whole activation, kernels/groupnorm.py:24-119)."""
+    if conv.groups != 1 or conv.dilation != (1, 1) or conv.stride[0] != conv.stride[1] \
+            or conv.padding[0] != conv.padding[1] or isinstance(conv.padding, str):
+        raise ValueError(f"conv2d_wrapper: unsupported convolution {conv}")
+    if upsample:
+        v = K.upsample_nearest2x(v)
+    return K.conv2d(v, conv.weight, conv.bias, stride=conv.stride[0], padding=conv.padding[0], temb=temb,
+                    residual=residual, nchw_output=False, w_static=True, gn_stats=True)
+
+
 def concat_wrapper(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return K.concat_channels(a, b)
 
@@ -90,5 +118,5 @@ def timestep_wrapper(t: torch.Tensor, num_channels: int) -> torch.Tensor:
 
 for _name in ("group_norm_wrapper", "layer_norm_wrapper", "linear_wrapper", "linear_wrapper_functional",
               "linear_geglu_wrapper", "geglu_wrapper", "attention_wrapper", "conv2d_wrapper", "concat_wrapper",
-              "timestep_wrapper"):
+              "timestep_wrapper", "linear_stats_wrapper", "conv2d_stats_wrapper"):
     torch.fx.wrap(_name)

@@ -18,8 +18,34 @@ def _count(name):
     CALLS[name] = CALLS.get(name, 0) + 1
 
 
-def groupnorm_wrapper(input, num_groups, weight, bias, eps, activation=False):
+def _partials(rows: torch.Tensor, rows_per_image: int):
+    """What the GEMM epilogue emits with gn_partial: (mean, M2) per 128-row tile and column, or None if not eligible."""
+    m, c = rows.shape
+    if K.gn_partial_rows(m, rows_per_image) == 0:
+        return None
+    t = rows.double().reshape(m // 128, 128, c)
+    mean = t.mean(dim=1)
+    m2 = ((t - mean[:, None, :]) ** 2).sum(dim=1)
+    return torch.stack([mean, m2], dim=-1).float().contiguous()
+
+
+def groupnorm_wrapper(input, num_groups, weight, bias, eps, activation=False, partials=None):
     _count("groupnorm")
+    if partials is not None and all(p is not None for p in partials):
+        # the statistics handed over by the producers must be THE statistics of `input` (right producer, right channel
+        # order of a concatenation): rebuild the group moments from them as gn_finalize_kernel does and compare
+        _count("groupnorm_from_partials")
+        n, c, h, w = input.shape
+        part = torch.cat(list(partials), dim=1).double()  # [tiles, C, 2]
+        assert part.shape == (n * h * w // 128, c, 2), (part.shape, input.shape)
+        tiles = h * w // 128
+        part = part.reshape(n, tiles, num_groups, c // num_groups, 2)
+        mean = part[..., 0].mean(dim=(1, 3))
+        m2 = (part[..., 1] + 128.0 * (part[..., 0] - mean[:, None, :, None]) ** 2).sum(dim=(1, 3))
+        var = m2 / (128.0 * tiles * (c // num_groups))
+        xg = input.double().reshape(n, num_groups, -1)
+        assert torch.allclose(mean, xg.mean(dim=2), rtol=1e-4, atol=1e-5), "partials: wrong mean"
+        assert torch.allclose(var, xg.var(dim=2, unbiased=False), rtol=1e-3, atol=1e-6), "partials: wrong variance"
     y = F.group_norm(input, num_groups, weight, bias, eps)
     return F.silu(y) if activation else y
 
@@ -30,7 +56,7 @@ def layer_norm(x, weight, bias, eps):
 
 
 def linear(x, weight, bias=None, activation=False, residual=None, geglu=False, silu_input=False, block_n=0,
-           w_static=False):
+           w_static=False, gn_stats=0):
     _count("linear_geglu" if geglu else "linear")
     if silu_input:
         x = F.silu(x)
@@ -43,6 +69,8 @@ def linear(x, weight, bias=None, activation=False, residual=None, geglu=False, s
     if residual is not None:
         assert residual.shape == y.shape, (residual.shape, y.shape)
         y = y + residual
+    if gn_stats:
+        return y, _partials(y.reshape(-1, y.shape[-1]), gn_stats)
     return y
 
 
@@ -68,7 +96,7 @@ def upsample_nearest2x(x):
 
 
 def conv2d(x, weight, bias, stride=1, padding=1, temb=None, residual=None, nchw_output=False, block_n=0,
-           w_static=False):
+           w_static=False, gn_stats=False):
     _count("conv2d")
     y = F.conv2d(x, weight, bias, stride=stride, padding=padding)
     if temb is not None:
@@ -77,6 +105,8 @@ def conv2d(x, weight, bias, stride=1, padding=1, temb=None, residual=None, nchw_
     if residual is not None:
         assert residual.shape == y.shape
         y = y + residual
+    if gn_stats:
+        return y, _partials(y.permute(0, 2, 3, 1).reshape(-1, y.shape[1]), y.shape[2] * y.shape[3])
     return y
 
 

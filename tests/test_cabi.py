@@ -32,16 +32,16 @@ def test_argument_validation_returns_error_codes(built_lib):
     from stabletriton_b200 import _cabi
     L = _cabi.lib()
     # null pointers
-    assert L.st_gemm_bf16(0, 64, 0, 64, 0, 64, 128, 128, 64, 0, 0, 0, 0, 0, 0) == -1
+    assert L.st_gemm_bf16(0, 64, 0, 64, 0, 64, 128, 128, 64, 0, 0, 0, 0, 0, 0, 0) == -1
     assert b"null" in L.st_last_error_string()
     # K not a multiple of 64
-    assert L.st_gemm_bf16(16, 72, 16, 72, 16, 128, 128, 128, 72, 0, 0, 0, 0, 0, 0) == -1
+    assert L.st_gemm_bf16(16, 72, 16, 72, 16, 128, 128, 128, 72, 0, 0, 0, 0, 0, 0, 0) == -1
     assert b"multiple of 64" in L.st_last_error_string()
     # misaligned pointer
-    assert L.st_gemm_bf16(8, 64, 16, 64, 16, 128, 128, 128, 64, 0, 0, 0, 0, 0, 0) == -1
+    assert L.st_gemm_bf16(8, 64, 16, 64, 16, 128, 128, 128, 64, 0, 0, 0, 0, 0, 0, 0) == -1
     assert b"aligned" in L.st_last_error_string()
     # GEGLU and SiLU are exclusive
-    assert L.st_gemm_bf16(16, 64, 16, 64, 16, 128, 128, 128, 64, 0, 0, 0, 3, 0, 0) == -1
+    assert L.st_gemm_bf16(16, 64, 16, 64, 16, 128, 128, 128, 64, 0, 0, 0, 3, 0, 0, 0) == -1
     # GroupNorm: channels not divisible by groups; too few channels per group
     assert L.st_groupnorm_nhwc_bf16(16, 16, 16, 16, 16, 1, 64, 320, 33, 1e-5, 1, 0) == -1
     assert L.st_groupnorm_nhwc_bf16(16, 16, 16, 16, 16, 1, 64, 64, 32, 1e-5, 1, 0) == -1
@@ -49,8 +49,8 @@ def test_argument_validation_returns_error_codes(built_lib):
     assert L.st_groupnorm_workspace_bytes(2, 16384, 321, 32) == 0
     # LayerNorm width, conv channel / spatial constraints, attention strides
     assert L.st_layernorm_bf16(16, 644, 16, 644, 16, 16, 8, 644, 1e-5, 0) == -1
-    assert L.st_conv3x3_nhwc_bf16(16, 16, 16, 16, 1, 16, 16, 60, 64, 0, 0, 0, 0, 0, 0) == -1
-    assert L.st_conv3x3_nhwc_bf16(16, 16, 16, 16, 1, 12, 12, 64, 64, 0, 0, 0, 0, 0, 0) == -1
+    assert L.st_conv3x3_nhwc_bf16(16, 16, 16, 16, 1, 16, 16, 60, 64, 0, 0, 0, 0, 0, 0, 0) == -1
+    assert L.st_conv3x3_nhwc_bf16(16, 16, 16, 16, 1, 12, 12, 64, 64, 0, 0, 0, 0, 0, 0, 0) == -1
     assert L.st_attention_bf16(16, 64, 64, 60, 16, 64, 64, 64, 16, 64, 64, 64, 16, 64, 64, 64, 1, 1, 8, 8, 0.125, 0) == -1
     assert L.st_linear_small_m_bf16(16, 64, 16, 64, 0, 16, 64, 33, 64, 64, 0, 0, 0, 0) == -1
 

@@ -37,7 +37,10 @@ def test_tiny_rewrite_leaves_no_module_calls_and_preserves_output():
     assert gm.get_buffer("_st_shared_proj_0").shape == (2 * (5 * 128 + 12 * 256), 128)
     assert not [k for k, _ in gm.named_buffers() if k.startswith("_st_fused_proj_")
                 and gm.get_buffer(k).shape[1] == 128 and gm.get_buffer(k).shape[0] in (256, 512)]
-    assert left["group_norm_wrapper"] == 46 and left["conv2d_wrapper"] == 51 and left["concat_wrapper"] == 9
+    # every GroupNorm takes its statistics from its producer's epilogue: 39 convs + 9 proj_out GEMMs emit them
+    assert gm.pass_report["fuse_group_norm_statistics"] == 46
+    assert left["group_norm_wrapper"] == 46 and left["concat_wrapper"] == 9
+    assert left["conv2d_wrapper"] + left["conv2d_stats_wrapper"] == 51 and left["linear_stats_wrapper"] == 9
     inp = synth.synth_inputs(2, 16, cfg, seed=5)
     with torch.no_grad():
         ref = model(**inp)[0]
@@ -46,6 +49,9 @@ def test_tiny_rewrite_leaves_no_module_calls_and_preserves_output():
     rel, cos = parity(out, ref)
     assert rel < 1e-5 and cos > 1 - 1e-9, (rel, cos)
     assert calls["attention"] == 34 and calls["conv2d"] == 51 and calls["groupnorm"] == 46
+    # at a 16x16 latent only the top level (256 pixels per image) has whole 128-row tiles per image; the fake GroupNorm
+    # checks every set of partials it receives against the statistics of its actual input
+    assert calls["groupnorm_from_partials"] >= 10
     # keeps the forward signature and the Diffusers config shim
     assert gm.config.in_channels == 4 and gm.config.addition_time_embed_dim == cfg.addition_time_embed_dim
     assert isinstance(gm(**inp) if False else [out], list)
@@ -93,7 +99,10 @@ def test_pass_counts_on_sdxl_architecture():
     assert not [k for k in census if k.startswith("module:")], census
     # 743 Linears: 70 GEGLU, the 17 resnet time-embedding projections batched into one GEMM, the rest 1:1
     assert report["fuse_time_embedding_projections"] == 1 and census["linear_wrapper_functional"] == 1
-    assert census["linear_geglu_wrapper"] + census["linear_wrapper"] == 743 - 17
+    assert census["linear_geglu_wrapper"] + census["linear_wrapper"] + census["linear_stats_wrapper"] == 743 - 17
+    # all 46 GroupNorms take their statistics from the epilogue of the conv / proj_out GEMM that wrote their input
+    assert report["fuse_group_norm_statistics"] == 46 and census["linear_stats_wrapper"] == 9
+    assert census["conv2d_stats_wrapper"] + census["conv2d_wrapper"] == 51
 
 
 @pytest.mark.skipif(not os.path.exists(REF_FILE), reason="reference not mounted")

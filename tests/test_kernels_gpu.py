@@ -265,3 +265,171 @@ def test_2048px_shapes(K):
     check(K.layer_norm(t, lw, lb, 1e-5).float().cpu(), F.layer_norm(t.float(), (640,), lw.float(), lb.float(), 1e-5).cpu())
     wl, bl = rnd(1920, 640, scale=640 ** -0.5, seed=59).cuda(), (rnd(1920, seed=60) * 0.1).cuda()
     check(K.linear(t, wl, bl).float().cpu(), F.linear(t.float(), wl.float(), bl.float()).cpu())
+
+
+# ---- GroupNorm statistics emitted by the producer's epilogue (round 2) -----------------------------------------------
+def _tile_stats(y_rows: torch.Tensor):
+    """(mean, M2) per 128-row tile and column of a [M, C] tensor, in float64 -- what gn_partial must hold."""
+    m, c = y_rows.shape
+    t = y_rows.double().reshape(m // 128, 128, c)
+    mean = t.mean(dim=1)
+    return mean, ((t - mean[:, None, :]) ** 2).sum(dim=1)
+
+
+def _check_partials(part, y_rows):
+    mean, m2 = _tile_stats(y_rows.cpu())
+    got = part.double().cpu()
+    assert got.shape == (mean.shape[0], mean.shape[1], 2)
+    assert torch.allclose(got[..., 0], mean, rtol=1e-5, atol=1e-5), (got[..., 0] - mean).abs().max()
+    assert torch.allclose(got[..., 1], m2, rtol=2e-3, atol=1e-3), ((got[..., 1] - m2).abs() / (m2.abs() + 1e-3)).max()
+
+
+@pytest.mark.parametrize("m,k,n,res,hw", [(2048, 1280, 1280, True, 1024), (8192, 640, 640, True, 4096),
+                                          (2048, 320, 200, False, 1024), (256, 64, 72, False, 128)])
+def test_gemm_epilogue_emits_groupnorm_partials(K, m, k, n, res, hw):
+    """st_gemm_bf16(gn_partial=...): per-tile column statistics of exactly the bf16 values it stores; the stored
+    output is bit-identical to the launch without them (the proj_out + residual -> norm1 site)."""
+    x, w, b = rnd(m, k, seed=50), rnd(n, k, scale=k ** -0.5, seed=51), rnd(n, seed=52) * 0.1
+    r = (rnd(m, n, seed=53) + 2.0) if res else None  # a residual with a non-zero mean: |mean| > sigma per column
+    args = (x.cuda(), w.cuda(), b.cuda())
+    kw = dict(residual=None if r is None else r.cuda())
+    plain = K.linear(*args, **kw)
+    y, part = K.linear(*args, **kw, gn_stats=hw)
+    assert torch.equal(y, plain)
+    _check_partials(part, y.float())
+    # shapes whose tiles would straddle images get no partials (the GroupNorm then makes its own pass)
+    y2, none = K.linear(*args, **kw, gn_stats=96)
+    assert none is None and torch.equal(y2, plain)
+
+
+@pytest.mark.parametrize("n,c,k,hw,mode", [(2, 320, 320, 128, "temb"), (2, 640, 640, 64, "res"),
+                                           (2, 1280, 1280, 32, "res"), (1, 64, 128, 16, "plain")])
+def test_conv_epilogue_emits_groupnorm_partials(K, n, c, k, hw, mode):
+    x, w, b = rnd(n, c, hw, hw, seed=21), rnd(k, c, 3, 3, scale=(9 * c) ** -0.5, seed=22), rnd(k, seed=23) * 0.1
+    temb = rnd(n, k, seed=24).cuda() if mode == "temb" else None
+    res = (rnd(n, k, hw, hw, seed=25) + 1.5).cuda().contiguous(memory_format=torch.channels_last) if mode == "res" else None
+    xg = x.cuda().contiguous(memory_format=torch.channels_last)
+    plain = K.conv2d(xg, w.cuda(), b.cuda(), temb=temb, residual=res)
+    y, part = K.conv2d(xg, w.cuda(), b.cuda(), temb=temb, residual=res, gn_stats=True)
+    assert torch.equal(y, plain)
+    _check_partials(part, y.permute(0, 2, 3, 1).reshape(-1, k).float())
+
+
+@pytest.mark.parametrize("n,c,hw,groups,silu,eps,offset", [
+    (2, 320, 128, 32, True, 1e-5, 0.5), (2, 640, 64, 32, True, 1e-5, 0.5), (2, 1280, 32, 32, False, 1e-6, 0.5),
+    (2, 320, 32, 32, False, 1e-5, 40.0),  # |mean| = 80 sigma: the tile-wise (mean, M2) form must not cancel
+    (16, 320, 32, 32, True, 1e-5, 0.5)])
+def test_groupnorm_from_producer_partials(K, n, c, hw, groups, silu, eps, offset):
+    """GroupNorm fed by the statistics of its producer: a 1x1 convolution writes x (and its partials), the GroupNorm
+    reads x once.  Must agree with the fp32 oracle on the SAME x and with the stand-alone two-pass kernel."""
+    src = rnd(n, 64, hw, hw, seed=60).cuda().contiguous(memory_format=torch.channels_last)
+    w1 = (rnd(c, 64, 1, 1, scale=0.125 if offset < 10 else 0.0625, seed=61)).cuda()
+    b1 = (rnd(c, seed=62) * 0.1 + offset).cuda()
+    x, part = K.conv2d(src, w1, b1, padding=0, gn_stats=True)
+    assert part is not None
+    gw, gb = (rnd(c, seed=2) * 0.1 + 1.0).cuda(), (rnd(c, seed=3) * 0.1).cuda()
+    got = K.groupnorm_wrapper(x, groups, gw, gb, eps, silu, partials=(part,))
+    alone = K.groupnorm_wrapper(x, groups, gw, gb, eps, silu)
+    ref = O.group_norm(x.float().cpu(), groups, gw.float().cpu(), gb.float().cpu(), eps, silu)
+    check(got.cpu(), ref, rel_tol=2e-2 if offset > 10 else 1.5e-2)
+    rel, _ = parity(got.float(), alone.float())
+    assert rel <= 1.6e-2  # the two kernels may differ by one bf16 ulp where the statistics differ in the last bits
+
+
+def test_groupnorm_of_a_concatenation_uses_both_producers_partials(K):
+    """Up-block site (unet_pt.py:356): norm1(cat([hidden, skip], 1)) -- the concatenation's statistics are its two
+    producers' partials side by side, also where a group straddles the seam (1280 + 640 channels, 60 per group)."""
+    n, hw = 2, 32
+    src = rnd(n, 64, hw, hw, seed=60).cuda().contiguous(memory_format=torch.channels_last)
+    a, pa = K.conv2d(src, rnd(1280, 64, 1, 1, scale=0.125, seed=61).cuda(), (rnd(1280, seed=62) + 0.3).cuda(), padding=0,
+                     gn_stats=True)
+    b, pb = K.conv2d(src, rnd(640, 64, 1, 1, scale=0.25, seed=63).cuda(), (rnd(640, seed=64) - 0.2).cuda(), padding=0,
+                     gn_stats=True)
+    x = K.concat_channels(a, b)
+    gw, gb = (rnd(1920, seed=2) * 0.1 + 1.0).cuda(), (rnd(1920, seed=3) * 0.1).cuda()
+    got = K.groupnorm_wrapper(x, 32, gw, gb, 1e-5, True, partials=(pa, pb))
+    ref = O.group_norm(x.float().cpu(), 32, gw.float().cpu(), gb.float().cpu(), 1e-5, True)
+    check(got.cpu(), ref, rel_tol=1.5e-2)
+    with pytest.raises(ValueError):
+        K.groupnorm_wrapper(x, 32, gw, gb, 1e-5, True, partials=(pa,))  # partials do not cover all channels
+
+
+def test_groupnorm_large_batch_is_processed_in_l2_sized_rounds(K):
+    """N = 16 at (320, 128^2) is 168 MB: statistics + apply run per group of images that fits the L2 window."""
+    x = (rnd(16, 320, 128, 128, seed=5) + 0.5).cuda().contiguous(memory_format=torch.channels_last)
+    w, b = (rnd(320, seed=2) * 0.1 + 1.0).cuda(), (rnd(320, seed=3) * 0.1).cuda()
+    got = K.groupnorm_wrapper(x, 32, w, b, 1e-5, True)
+    ref = F.silu(F.group_norm(x.float(), 32, w.float(), b.float(), 1e-5))
+    check(got.cpu(), ref.cpu(), rel_tol=1.5e-2)
+
+
+def test_two_captured_graphs_with_groupnorm_replay_concurrently(K):
+    """the last-CTA tickets of the stand-alone GroupNorm live in the call's own workspace, so two captured
+    graphs (each with its own pool) replayed at the same time on two streams cannot disturb each other."""
+    w, b = (rnd(320, seed=72) * 0.1 + 1.0).cuda(), (rnd(320, seed=73) * 0.1).cuda()
+    xs = [rnd(2, 320, 64, 64, seed=80 + i).cuda().contiguous(memory_format=torch.channels_last) for i in range(2)]
+    ref = [K.groupnorm_wrapper(x, 32, w, b, 1e-5, True) for x in xs]
+    graphs, outs, streams = [], [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for i in range(2):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(streams[i]):
+            K.groupnorm_wrapper(xs[i], 32, w, b, 1e-5, True)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=streams[i]):
+                y = xs[i]
+                for _ in range(8):  # a chain of GroupNorms keeps each graph busy for a while
+                    y = K.groupnorm_wrapper(xs[i], 32, w, b, 1e-5, True)
+        graphs.append(g)
+        outs.append(y)
+    torch.cuda.synchronize()
+    for _ in range(50):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                graphs[i].replay()
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert torch.equal(outs[i], ref[i])
+
+
+def test_outputs_do_not_overrun_and_repeat_bit_for_bit(K):
+    """compute-sanitizer is closed on the GPU pool, so the memcheck / racecheck role is played by canaries and
+    repetition: every kernel family writes into a buffer embedded in sentinel-filled memory (TMA stores clipped at
+    ragged edges, strided epilogues) and is run 20 times -- any out-of-bounds store trips a sentinel, any shared-memory
+    race between the TMA / MMA / epilogue warps shows up as a run-to-run difference."""
+    torch.manual_seed(0)
+
+    def guarded(fn, reps=20):
+        first = None
+        for i in range(reps):
+            torch.cuda.empty_cache()
+            pad = torch.full((1 << 20,), -7.0, dtype=torch.bfloat16, device="cuda")  # neighbours in the caching allocator
+            out = fn()
+            pad2 = torch.full((1 << 20,), -7.0, dtype=torch.bfloat16, device="cuda")
+            torch.cuda.synchronize()
+            assert bool((pad == -7.0).all()) and bool((pad2 == -7.0).all()), "sentinel overwritten"
+            assert torch.isfinite(out.float()).all()
+            if first is None:
+                first = out.clone()
+            else:
+                assert torch.equal(out, first), f"run {i} differs from run 0"
+            del pad, pad2
+        return first
+
+    x, w, b = rnd(300, 192, seed=1).cuda(), rnd(328, 192, scale=0.07, seed=2).cuda(), rnd(328, seed=3).cuda()
+    r = rnd(300, 328, seed=4).cuda()
+    guarded(lambda: K.linear(x, w, b, residual=r))                       # ragged M and N, TMA-store clipping
+    xg, wg, bg = rnd(384, 128, seed=5).cuda(), rnd(512, 128, scale=0.09, seed=6).cuda(), rnd(512, seed=7).cuda()
+    guarded(lambda: K.linear(xg, wg, bg, geglu=True))
+    xc = rnd(2, 64, 16, 16, seed=8).cuda().contiguous(memory_format=torch.channels_last)
+    wc, bc = rnd(192, 64, 3, 3, scale=1 / 24, seed=9).cuda(), rnd(192, seed=10).cuda()
+    guarded(lambda: K.conv2d(xc, wc, bc, temb=rnd(2, 192, seed=11).cuda()))
+    guarded(lambda: K.conv2d(xc, wc, bc, gn_stats=True)[1])
+    q, k, v = rnd(1, 300, 128, seed=12).cuda(), rnd(1, 300, 128, seed=13).cuda(), rnd(1, 300, 128, seed=14).cuda()
+    guarded(lambda: K.attention_btc(q, k, v, 2, 0.125))                  # pipelined kernel, ragged Tq / Tk
+    kc, vc = rnd(1, 77, 128, seed=15).cuda(), rnd(1, 77, 128, seed=16).cuda()
+    guarded(lambda: K.attention_btc(q, kc, vc, 2, 0.125))                # one-block kernel
+    xn = rnd(2, 320, 20, 20, seed=17).cuda().contiguous(memory_format=torch.channels_last)
+    gw, gb = rnd(320, seed=18).cuda(), rnd(320, seed=19).cuda()
+    guarded(lambda: K.groupnorm_wrapper(xn, 32, gw, gb, 1e-5, True))
+    xl = rnd(77, 640, seed=20).cuda()
+    guarded(lambda: K.layer_norm(xl, rnd(640, seed=21).cuda(), rnd(640, seed=22).cuda(), 1e-5))
