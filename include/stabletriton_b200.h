@@ -60,8 +60,7 @@ int st_set_workspace(void* ptr, size_t bytes);
  * wrong.  x, y: [N, HW, C] bf16; gamma, beta: [C] bf16; C % groups == 0, C % 8 == 0.
  * workspace: st_groupnorm_workspace_bytes() bytes of scratch, 16-byte aligned, owned by THIS call (per-image arrival
  * tickets, partial statistics, per-channel scale / shift all live there -- no library-global state, so concurrent calls
- * on different streams or in different captured graphs never interact).  Contents on entry are irrelevant.
- * Activations larger than 48 MB are processed in image groups so that the normalise pass finds its input in L2. */
+ * on different streams or in different captured graphs never interact).  Contents on entry are irrelevant. */
 size_t st_groupnorm_workspace_bytes(int N, int HW, int C, int groups);
 int st_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, void* workspace, int N,
                            int HW, int C, int groups, float eps, int apply_silu, st_stream_t stream);

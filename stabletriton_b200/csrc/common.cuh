@@ -32,7 +32,7 @@ struct PerDeviceOnce {
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with row pitch ld (elements);
 // box = [box_rows, 64 cols], 128-byte swizzle.  Returns 0 on success.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                 uint32_t box_cols = 64);
+                 uint32_t box_cols = 64, bool swizzle128 = true);
 // 4-D bf16 tensor map over an NHWC activation [N, H, W, C] (C contiguous); box = [Nt, Ht, Wt, 64].
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t Ht,
                    uint32_t Wt, uint32_t Nt = 1);

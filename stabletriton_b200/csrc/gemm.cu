@@ -6,72 +6,79 @@
 
 namespace st {
 
-// Tile-width choice from the measured cost model (profiles/r01_gemm_trace.txt, tools/mmabench.cu): per 64-wide
-// k-block a CTA needs max(tensor pipe, operand fill) cycles, where the tensor pipe takes 4 x BLOCK_N/2 cycles
-// (128 x N x 16 runs at its N/2 floor with the warp-convergent issue loop) and the fill moves (128 + BLOCK_N) x
-// 128 bytes at min(88 B/clk per SM, 9.6 KB/clk over all CTAs) out of L2; the epilogue costs a few cycles per
-// output column, and tiles are spread over the SMs in waves.  Ties go to the narrower tile.
-static bool cluster_allowed() {
-  static const bool v = [] {
-    // Experimental, opt-in (ST_GEMM_CLUSTER=1).  Measured on B200 (profiles/r01_gemm_trace.txt): correct, and the
-    // 256 x 256 x 16 pair MMA runs at its 128-cycle floor (tools/mmabench2.cu), but at 148 CTAs the main loop only
-    // goes from 664 to 640 cycles per k-block while cluster launch + pair TMEM allocation + two cluster barriers
-    // add ~1.2 k cycles of set-up per launch: 1070 vs 1250 TFLOP/s on the 2048 x 10240 x 1280 GEGLU projection.
+// Tile shape from the measured cost model (profiles/r01_gemm_trace.txt, profiles/r02_gemm_pairs.txt, tools/mmabench*.cu).
+// Per 64-wide k-block a CTA needs max(tensor pipe, operand fill) cycles: the tensor pipe takes 4 x BLOCK_N/2 cycles
+// (a 128 x N x 16 -- or, for a CTA pair, 256 x N x 16 -- tcgen05.mma runs at its N/2 floor with the warp-convergent
+// issue loop); the fill moves (128 + BLOCK_N) x 128 bytes per CTA (pair: 128 + BLOCK_N/2 rows, each CTA stages half
+// of the weight tile) at min(88 B/clk into one SM, ~9.6 KB/clk out of L2 for all CTAs together).  At full occupancy
+// the one-CTA 128 x 256 loop is L2-fill bound (664-760 cycles against 512), which CTA pairs (cta_group::2) remove:
+// 8192^3 1351 -> 1465 TFLOP/s, GEGLU 2048 x 10240 x 1280 1242 -> 1331.  A pair launch costs ~1.5 k cycles more set-up
+// (cluster scheduling, pair TMEM allocation, two cluster barriers), so short single-wave GEMMs stay unpaired.
+// ST_GEMM_CLUSTER=0 / 1 forces pairs off / on wherever they are possible; default: the model decides per shape.
+static int cluster_policy() {
+  static const int v = [] {
     const char* e = getenv("ST_GEMM_CLUSTER");
-    return e && e[0] == '1';
+    if (!e || !e[0]) return 2;
+    return e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2);
   }();
   return v;
 }
 
-// CTA pairs (cta_group::2 MMA, each CTA stages half of the weight tile): vertically adjacent tiles must pair up,
-// the half tile must keep the 1024-byte swizzle alignment, and it only pays once the grid is large enough to hit
-// the aggregate L2 feed limit (below ~96 CTAs the 128x256 loop is tensor-pipe bound anyway).
-static bool want_cluster(int M, int n_cols, int block_n, bool geglu) {
-  if (!cluster_allowed()) return false;
+static bool pair_possible(int M, int block_n, bool geglu) {
   const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-  if (mb % 2 != 0) return false;
-  if (geglu ? block_n != 256 : (block_n != 256 && block_n != 192)) return false;
-  const int out_cols = geglu ? block_n / 2 : block_n;
-  const long tiles = (long)mb * ((n_cols + out_cols - 1) / out_cols);
-  return tiles >= 96;
+  if (mb % 2 != 0) return false;  // vertically adjacent tiles pair up
+  return geglu ? block_n == 256 : (block_n == 256 || block_n == 192 || block_n == 160);
 }
 
-static int choose_block_n(int M, int n_cols, bool geglu, int K) {
-  const int sms = device_sm_count();
+struct TileChoice {
+  int block_n;
+  bool pair;
+};
+
+static double tile_cost(int M, int n_cols, bool geglu, int K, int bn, bool pair, int sms) {
   const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-  const int cands_plain[4] = {64, 128, 192, 256};
+  const int out_cols = geglu ? bn / 2 : bn;
+  const int nb = (n_cols + out_cols - 1) / out_cols;
+  const long tiles = (long)mb * nb;
+  const long waves = (tiles + sms - 1) / sms;
+  const double ctas = tiles < sms ? (double)tiles : (double)sms;
+  const double l2_bytes = 128.0 * 128.0 + (pair ? 64.0 : 128.0) * bn;  // per CTA and k-block, out of L2
+  const double fill_l2 = l2_bytes / (9600.0 / ctas);
+  const double fill_sm = l2_bytes / 88.0;
+  const double fill = fill_l2 > fill_sm ? fill_l2 : fill_sm;
+  const double mma = 2.0 * bn;
+  const double per_tile = (fill > mma ? fill : mma) * (K / 64) + 1500.0 + 10.0 * out_cols;
+  return waves * per_tile + (pair ? 1500.0 : 0.0);
+}
+
+static TileChoice choose_tile(int M, int n_cols, bool geglu, int K, bool allow_pair) {
+  const int sms = device_sm_count();
+  const int cands_plain[5] = {64, 128, 160, 192, 256};
   const int cands_geglu[2] = {128, 256};
   const int* cands = geglu ? cands_geglu : cands_plain;
-  const int ncand = geglu ? 2 : 4;
-  int best = 256;
+  const int ncand = geglu ? 2 : 5;
+  const int policy = allow_pair ? cluster_policy() : 0;
+  TileChoice best{256, false};
   double best_cost = 1e30;
   for (int i = 0; i < ncand; ++i) {
     const int bn = cands[i];
-    const int out_cols = geglu ? bn / 2 : bn;
-    const int nb = (n_cols + out_cols - 1) / out_cols;
-    const long tiles = (long)mb * nb;
-    const long waves = (tiles + sms - 1) / sms;
-    const double ctas = tiles < sms ? (double)tiles : (double)sms;
-    const bool cluster = want_cluster(M, n_cols, bn, geglu);
-    const double l2_bytes = 128.0 * 128.0 + (cluster ? 64.0 : 128.0) * bn;  // per CTA and k-block, out of L2
-    const double sm_bytes = cluster ? l2_bytes : (128.0 + bn) * 128.0;      // into one SM
-    const double fill_l2 = l2_bytes / (9600.0 / ctas);
-    const double fill_sm = sm_bytes / 88.0;
-    const double fill = fill_l2 > fill_sm ? fill_l2 : fill_sm;
-    const double mma = 2.0 * bn;
-    const double tile_cost = (fill > mma ? fill : mma) * (K / 64) + 1500.0 + 10.0 * out_cols;
-    const double cost = waves * tile_cost;
-    if (cost < best_cost * 0.97) {
-      best_cost = cost;
-      best = bn;
+    for (int pair = 0; pair < 2; ++pair) {
+      if (pair && (policy == 0 || !pair_possible(M, bn, geglu))) continue;
+      if (!pair && policy == 1 && pair_possible(M, bn, geglu)) continue;
+      if (!pair && bn == 160) continue;  // 160 only pays as a pair tile (un-paired it is fill-bound like 192)
+      const double cost = tile_cost(M, n_cols, geglu, K, bn, pair != 0, sms);
+      if (cost < best_cost * 0.97) {  // ties go to the narrower / un-paired tile
+        best_cost = cost;
+        best = TileChoice{bn, pair != 0};
+      }
     }
   }
   return best;
 }
 
 template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false, bool kCluster = false>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdt,
+                       const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES, kCluster>;
   auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu, kStreamK, kCluster>;
   static PerDeviceOnce configured;  // per instantiation AND per device (function attributes live in the context)
@@ -97,37 +104,39 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     const int pair_tiles = tiles / 2;
     grid = 2 * (pair_tiles < sms / 2 ? pair_tiles : sms / 2);
   }
-  launch_kernel_cluster(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, kCluster ? 2 : 1, ta, tb, td, p);
+  launch_kernel_cluster(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, kCluster ? 2 : 1, ta, tb, td, tdt, p);
   ST_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return ST_OK;
 }
 
 template <bool kConvA>
-static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
-                         int block_n, bool geglu, cudaStream_t stream) {
+static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdt,
+                         const GemmParams& p, int block_n, bool geglu, cudaStream_t stream) {
   if (p.cluster) {
-    if (geglu && block_n == 256) return launch_gemm<256, 6, kConvA, true, false, true>(ta, tb, td, p, stream);
-    if (!geglu && block_n == 256) return launch_gemm<256, 6, kConvA, false, false, true>(ta, tb, td, p, stream);
-    if (!geglu && block_n == 192) return launch_gemm<192, 7, kConvA, false, false, true>(ta, tb, td, p, stream);
+    if (geglu && block_n == 256) return launch_gemm<256, 6, kConvA, true, false, true>(ta, tb, td, tdt, p, stream);
+    if (!geglu && block_n == 256) return launch_gemm<256, 6, kConvA, false, false, true>(ta, tb, td, tdt, p, stream);
+    if (!geglu && block_n == 192) return launch_gemm<192, 7, kConvA, false, false, true>(ta, tb, td, tdt, p, stream);
+    if (!geglu && block_n == 160) return launch_gemm<160, 7, kConvA, false, false, true>(ta, tb, td, tdt, p, stream);
     set_error("gemm: no cluster instantiation for block_n %d", block_n);
     return ST_ERR_INVALID_ARGUMENT;
   }
   if (geglu) {
     switch (block_n) {
-      case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, td, p, stream);
-      case 128: return launch_gemm<128, 6, kConvA, true>(ta, tb, td, p, stream);
+      case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, td, tdt, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, true>(ta, tb, td, tdt, p, stream);
     }
   } else {
     switch (block_n) {
       case 256:
-        if (p.stream_k) return launch_gemm<256, 4, kConvA, false, true>(ta, tb, td, p, stream);
-        return launch_gemm<256, 4, kConvA, false>(ta, tb, td, p, stream);
-      case 192: return launch_gemm<192, 5, kConvA, false>(ta, tb, td, p, stream);
-      case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, td, p, stream);
-      case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, td, p, stream);
+        if (p.stream_k) return launch_gemm<256, 4, kConvA, false, true>(ta, tb, td, tdt, p, stream);
+        return launch_gemm<256, 4, kConvA, false>(ta, tb, td, tdt, p, stream);
+      case 192: return launch_gemm<192, 5, kConvA, false>(ta, tb, td, tdt, p, stream);
+      case 160: return launch_gemm<160, 5, kConvA, false>(ta, tb, td, tdt, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, td, tdt, p, stream);
+      case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, td, tdt, p, stream);
     }
   }
-  set_error("gemm: unsupported block_n %d (use 0, 128 or 256; 64 and 192 without GEGLU)", block_n);
+  set_error("gemm: unsupported block_n %d (0, 64, 128, 160, 192 or 256; GEGLU: 128 or 256)", block_n);
   return ST_ERR_INVALID_ARGUMENT;
 }
 
@@ -192,14 +201,24 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   float* sk_ws = nullptr;
   unsigned* sk_flags = nullptr;
   bool stream_k = false;
+  bool pair = false;
   if (block_n == 0) {
-    block_n = choose_block_n(M, n_out, geglu, K);
+    const TileChoice tc = choose_tile(M, n_out, geglu, K, /*allow_pair=*/true);
+    block_n = tc.block_n;
+    pair = tc.pair;
     const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-    if (!geglu && !gn_partial && want_stream_k(mb * ((n_out + 255) / 256), K / kGemmBlockK, mb * ((n_out + block_n - 1) / block_n),
+    if (!geglu && !gn_partial && !pair && want_stream_k(mb * ((n_out + 255) / 256), K / kGemmBlockK, mb * ((n_out + block_n - 1) / block_n),
                                 &sk_ws, &sk_flags)) {
       stream_k = true;
       block_n = 256;
     }
+  } else if (block_n < 0) {  // negative: force a CTA-pair launch with tile width -block_n (tests, tuning)
+    block_n = -block_n;
+    ST_CHECK_ARG(pair_possible(M, block_n, geglu), "gemm: a pair launch needs an even number of row "
+                 "blocks and block_n 256 / 192 / 160 (GEGLU: 256); got M = %d, block_n = %d", M, block_n);
+    pair = true;
+  } else if (cluster_policy() == 1 && pair_possible(M, block_n, geglu)) {
+    pair = true;
   }
   const int out_cols = geglu ? block_n / 2 : block_n;
 
@@ -223,7 +242,7 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
   p.ws = sk_ws;
   p.flags = sk_flags;
-  p.cluster = (!stream_k && !gn_partial && want_cluster(M, n_out, block_n, geglu)) ? 1 : 0;
+  p.cluster = pair ? 1 : 0;
   p.gn_part = static_cast<float*>(gn_partial);
 
   CUtensorMap ta, tb;
@@ -231,10 +250,12 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   if (rc != ST_OK) return rc;
   rc = make_tmap_2d(&tb, W, N, K, ldw, (geglu || p.cluster) ? block_n / 2 : block_n);  // one box per B load
   if (rc != ST_OK) return rc;
-  CUtensorMap td;
+  CUtensorMap td, tdt;
   rc = make_tmap_2d(&td, D, M, n_out, ldd, kGemmBlockM);
   if (rc != ST_OK) return rc;
-  return dispatch_gemm<false>(ta, tb, td, p, block_n, geglu, static_cast<cudaStream_t>(stream));
+  rc = make_tmap_2d(&tdt, D, M, n_out, ldd, kGemmBlockM, 32, /*swizzle128=*/false);  // 32-column tail group of a 160-wide tile
+  if (rc != ST_OK) return rc;
+  return dispatch_gemm<false>(ta, tb, td, tdt, p, block_n, geglu, static_cast<cudaStream_t>(stream));
 }
 
 int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int C, int K,
@@ -270,14 +291,24 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   float* sk_ws = nullptr;
   unsigned* sk_flags = nullptr;
   bool stream_k = false;
+  bool pair = false;
   if (block_n == 0) {
-    block_n = choose_block_n(M, K, false, 9 * C);
+    const TileChoice tc = choose_tile(M, K, false, 9 * C, /*allow_pair=*/true);
+    block_n = tc.block_n;
+    pair = tc.pair;
     const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-    if (!gn_partial && want_stream_k(mb * ((K + 255) / 256), 9 * C / kGemmBlockK, mb * ((K + block_n - 1) / block_n), &sk_ws,
+    if (!gn_partial && !pair && want_stream_k(mb * ((K + 255) / 256), 9 * C / kGemmBlockK, mb * ((K + block_n - 1) / block_n), &sk_ws,
                       &sk_flags)) {
       stream_k = true;
       block_n = 256;
     }
+  } else if (block_n < 0) {
+    block_n = -block_n;
+    ST_CHECK_ARG(pair_possible(M, block_n, false), "conv3x3: a pair launch needs an even number of "
+                 "row blocks and block_n 256 / 192 / 160; got N*H*W = %d, block_n = %d", M, block_n);
+    pair = true;
+  } else if (cluster_policy() == 1 && pair_possible(M, block_n, false)) {
+    pair = true;
   }
 
   GemmParams p{};
@@ -301,7 +332,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.w_static = (flags & ST_W_STATIC) ? 1 : 0;
   p.ws = sk_ws;
   p.flags = sk_flags;
-  p.cluster = (!stream_k && !gn_partial && want_cluster(N * H * W, K, block_n, false)) ? 1 : 0;
+  p.cluster = pair ? 1 : 0;
   p.gn_part = static_cast<float*>(gn_partial);
   p.conv_H = H;
   p.conv_W = W;
@@ -314,10 +345,12 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   if (rc != ST_OK) return rc;
   rc = make_tmap_2d(&tb, w, K, 9 * (uint64_t)C, 9 * (uint64_t)C, p.cluster ? block_n / 2 : block_n);
   if (rc != ST_OK) return rc;
-  CUtensorMap td;
+  CUtensorMap td, tdt;
   rc = make_tmap_2d(&td, y, M, K, K, kGemmBlockM);
   if (rc != ST_OK) return rc;
-  return dispatch_gemm<true>(ta, tb, td, p, block_n, false, static_cast<cudaStream_t>(stream));
+  rc = make_tmap_2d(&tdt, y, M, K, K, kGemmBlockM, 32, /*swizzle128=*/false);
+  if (rc != ST_OK) return rc;
+  return dispatch_gemm<true>(ta, tb, td, tdt, p, block_n, false, static_cast<cudaStream_t>(stream));
 }
 
 int st_set_workspace(void* ptr, size_t bytes) {
@@ -330,6 +363,12 @@ int st_set_workspace(void* ptr, size_t bytes) {
 
 size_t st_workspace_bytes(void) {
   return static_cast<size_t>(st::device_sm_count()) * st::kGemmBlockM * 256 * sizeof(float);
+}
+
+// Debug hook: the launcher's tile choice for a shape -- block_n, or -block_n for a CTA-pair launch.
+int st_debug_choose_tile(int M, int n_cols, int geglu, int K) {
+  const st::TileChoice tc = st::choose_tile(M, n_cols, geglu != 0, K, true);
+  return tc.pair ? -tc.block_n : tc.block_n;
 }
 
 // Debug hook (not part of the product surface): when set, every GEMM/conv CTA writes 8 clock64 stamps

@@ -122,13 +122,17 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
 template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false, bool kCluster = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d_tail,
+                    const GemmParams p) {
   using S = GemmSmem<BLOCK_N, STAGES, kCluster>;
   constexpr int kAccCols = BLOCK_N;                       // fp32 accumulator columns per stage
   constexpr int kTmemCols = tmem_cols_for(2 * kAccCols);  // two accumulator stages
   static_assert(2 * kAccCols <= 512, "accumulator stages exceed TMEM");
   static_assert(!(kStreamK && kCluster), "stream-K and cluster multicast are exclusive");
-  static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "BLOCK_N");
+  // Tile widths that are not a multiple of 64 (160: eight tiles across N = 1280, so 128 CTAs instead of 112 carry the
+  // 2048 x 1280 outputs) end in a 32-column group, stored through tmap_d_tail (un-swizzled 32-column boxes).
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "BLOCK_N");
+  static_assert(!kStreamK || BLOCK_N % 64 == 0, "stream-K assumes whole 64-column groups");
   static_assert(!kGeglu || BLOCK_N % 128 == 0, "the TMA store works on 64-column groups of the output tile");
 
   extern __shared__ uint8_t smem_raw[];
@@ -189,6 +193,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_d);
+    if (BLOCK_N % 64 != 0) tma_prefetch_desc(&tmap_d_tail);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -370,7 +375,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int kOutCols = kGeglu ? BLOCK_N / 2 : BLOCK_N;
-    constexpr int kGroups = kOutCols / 64;   // 64-column groups = TMA store boxes
+    constexpr int kGroups = (kOutCols + 63) / 64;   // 64-column groups = TMA store boxes
+    constexpr bool kTail = kOutCols % 64 != 0;       // the last group is only 32 columns wide
     // the time-embedding row can be folded into the staged bias when a tile lies inside one image
     const bool rowbias_per_tile = p.rowbias != nullptr && p.rows_per_batch >= kGemmBlockM;
     const bool rowbias_per_row = p.rowbias != nullptr && !rowbias_per_tile;
@@ -388,7 +394,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // each 64-column group gets its own 16 KB staging tile there instead of sharing one.  That removes, per
       // group, the wait for the previous bulk store to finish reading the tile and one of the two 256-thread
       // barriers, on the only epilogue that is not hidden behind a following main loop.
-      const bool ring_staging = !kStreamK && !kCluster && cursor >= num_tiles && kGroups * S::kOutStageBytes <= STAGES * S::kStageBytes;
+      // (CTA pairs: the accumulator barrier is the pair-wide commit of the last MMA, so BOTH rings are idle by then.)
+      const bool last_tile = kCluster ? cursor >= (p.num_m_blocks >> 1) * p.num_n_blocks : cursor >= num_tiles;
+      const bool ring_staging = !kStreamK && last_tile && kGroups * S::kOutStageBytes <= STAGES * S::kStageBytes;
       float* sb = s_bias + acc * BLOCK_N;
       const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
 
@@ -485,7 +493,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) {
         if (n0 + g * 64 >= p.n_out) break;  // this 64-column group lies entirely past the matrix edge
-        const int c = g * 64 + half * 32;   // first tile column of this thread's chunk
+        // 32-column tail group: the warps of the upper half have no columns of their own; they shadow the lower
+        // half's (same barriers, no stores), which keeps the group loop free of divergent synchronisation
+        const bool tail = kTail && g == kGroups - 1;
+        const bool dead = tail && half == 1;
+        const int c = g * 64 + (dead ? 0 : half * 32);   // first tile column of this thread's chunk
         uint32_t v[32];
         uint32_t gt[32];
         tmem_ld_32x32b_x32(t_row + c, v);
@@ -570,8 +582,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           o.z = pack_bf16x2(x[j + 4], x[j + 5]);
           o.w = pack_bf16x2(x[j + 6], x[j + 7]);
           const int chunk = half * 4 + (j >> 3);
-          *reinterpret_cast<uint4*>(s_stage + tile_row * 128 + ((chunk ^ (tile_row & 7)) << 4)) = o;
-          if (!kGeglu && !kStreamK && !kCluster && p.gn_part) {  // keep the ROUNDED values: the statistics are those of the stored tensor
+          if (tail) {  // un-swizzled [128 rows][32 cols]
+            if (!dead) *reinterpret_cast<uint4*>(s_stage + tile_row * 64 + ((j >> 3) << 4)) = o;
+          } else {
+            *reinterpret_cast<uint4*>(s_stage + tile_row * 128 + ((chunk ^ (tile_row & 7)) << 4)) = o;
+          }
+          if (!kGeglu && !kStreamK && p.gn_part) {  // keep the ROUNDED values: the statistics are those of the stored tensor
             const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -581,7 +597,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         float* gn_slot = s_gn + (g & 1) * (4 * 64 * 2);
-        if (!kGeglu && !kStreamK && !kCluster && p.gn_part) {
+        if (!kGeglu && !kStreamK && p.gn_part) {
           // (mean, M2) of my 32 columns over this warp's 32 rows -> shared memory; merged over the 4 lane quadrants
           // after the barrier below (no extra synchronisation: see the buffer parity)
           float sq[32];
@@ -591,21 +607,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const float s2 = warp_column_sums(sq, lane);
           const float mean = s1 * (1.f / 32.f);
           const float m2 = fmaxf(s2 - s1 * mean, 0.f);
-          *reinterpret_cast<float2*>(gn_slot + (quad * 64 + half * 32 + lane) * 2) = make_float2(mean, m2);
+          if (!dead) *reinterpret_cast<float2*>(gn_slot + (quad * 64 + half * 32 + lane) * 2) = make_float2(mean, m2);
         }
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(9);
         // 64 columns staged: hand them to the TMA store engine (clips rows >= M and columns >= n_out)
         fence_proxy_async_smem();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (etid == 0) {
-          tma_store_2d(&tmap_d, s_stage, n0 + g * 64, m_blk * kGemmBlockM);
+          tma_store_2d(tail ? &tmap_d_tail : &tmap_d, s_stage, n0 + g * 64, m_blk * kGemmBlockM);
           tma_store_commit();
         }
-        if (!kGeglu && !kStreamK && !kCluster && p.gn_part && etid >= 64 && etid < 128) {
+        if (!kGeglu && !kStreamK && p.gn_part && etid >= 64 && etid < 128) {
           // one thread per column: merge the four 32-row partials (equal counts), fixed order
           const int col = etid - 64;
           const int gcol = n0 + g * 64 + col;
-          if (gcol < p.n_out) {
+          if (gcol < p.n_out && !(tail && col >= 32)) {
             float2 q[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const float2*>(gn_slot + (i * 64 + col) * 2);

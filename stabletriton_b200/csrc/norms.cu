@@ -48,9 +48,10 @@ constexpr int kGnApplyPixPerThread = 6;
 // captured graphs replayed at once -- necessarily own different workspaces, so they can never see each other's
 // tickets (a library-global table, however it is indexed, cannot promise that), and a faulted launch leaves nothing
 // behind.
-// An activation larger than this is processed in image groups of at most this many bytes (statistics, then apply, per
-// group), so that the apply pass still finds its input in the 126 MB L2: one HBM read + one write whatever N is.
-constexpr size_t kGnL2WindowBytes = 48u << 20;
+// (Measured and rejected, r02: processing a large batch in L2-sized image groups -- statistics, then apply, per 48 MB
+// group, so that the apply pass finds its input in L2 -- makes every launch latency-bound again: N = 16 at
+// (320, 128^2) 122 -> 164 us.  One round whatever N is.)
+constexpr size_t kGnL2WindowBytes = ~static_cast<size_t>(0);
 
 struct GnGeom {
   int N, HW, C, G, cpg;
@@ -276,18 +277,23 @@ gn_ticket_zero_kernel(unsigned int* __restrict__ tickets, int n) {
 // M2 = sum(M2_i) + 128 * sum((mean_i - mean)^2), evaluated in a fixed order -- and writes per-channel scale / shift;
 // gn_apply_kernel then streams the activation ONCE.  A channel concatenation (up-block skip connections) never has
 // to be reduced again: channels [0, C_a) come from the first producer's partials, [C_a, C) from the second's.
-// One warp per (image, group).
+// One CTA of 128 threads per (image, group); a single pass over the partials with every load independent of the
+// previous one (the first version walked them with one dependent L2 round trip per entry and took 20 us):
+// shift = the first partial mean of the group, d_i = mean_i - shift, then
+//     mean = shift + sum(d_i) / k,      M2 = sum(M2_i) + 128 * (sum(d_i^2) - sum(d_i)^2 / k)
+// which cannot cancel (|d_i| is of the order of the spread of the tile means, not of |mean|).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kGnFinThreads = 128;
+__global__ void __launch_bounds__(kGnFinThreads)
 gn_finalize_kernel(const float* __restrict__ part_a, int C_a, const float* __restrict__ part_b, int C_b,
                    const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                    float* __restrict__ scale_shift, int tiles, int C, int G, int cpg, float eps) {
   pdl_launch_dependents();
   pdl_wait();
+  __shared__ float s_red[3][kGnFinThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int g = blockIdx.x;
   const int n = blockIdx.y;
-  if (g >= G) return;
   const int entries = tiles * cpg;
   auto entry = [&](int idx) -> float2 {
     const int t = idx / cpg;
@@ -296,19 +302,45 @@ gn_finalize_kernel(const float* __restrict__ part_a, int C_a, const float* __res
     const float* src = ch < C_a ? part_a + (tile * C_a + ch) * 2 : part_b + (tile * C_b + (ch - C_a)) * 2;
     return __ldcg(reinterpret_cast<const float2*>(src));
   };
-  float msum = 0.f;
-  for (int i = lane; i < entries; i += 32) msum += entry(i).x;
-  msum = warp_sum(msum);
-  const float mean = msum / static_cast<float>(entries);
-  float m2 = 0.f;
-  for (int i = lane; i < entries; i += 32) {
-    const float2 e = entry(i);
-    const float d = e.x - mean;
-    m2 += fmaf(128.f * d, d, e.y);
+  const float shift = entry(0).x;
+  float sd = 0.f, sdd = 0.f, sm2 = 0.f;
+  constexpr int kBatch = 8;  // independent loads in flight per thread
+  for (int base = threadIdx.x; base < entries; base += kBatch * kGnFinThreads) {
+    float2 e[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int i = base + j * kGnFinThreads;
+      e[j] = i < entries ? entry(i) : make_float2(shift, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const float d = e[j].x - shift;
+      sd += d;
+      sdd = fmaf(d, d, sdd);
+      sm2 += e[j].y;
+    }
   }
-  m2 = warp_sum(m2);
-  const float rstd = rsqrtf(m2 / (128.f * static_cast<float>(entries)) + eps);  // biased variance, as torch.nn.GroupNorm
-  for (int c = lane; c < cpg; c += 32) {
+  sd = warp_sum(sd);
+  sdd = warp_sum(sdd);
+  sm2 = warp_sum(sm2);
+  if (lane == 0) {
+    s_red[0][warp] = sd;
+    s_red[1][warp] = sdd;
+    s_red[2][warp] = sm2;
+  }
+  __syncthreads();
+  float tsd = 0.f, tsdd = 0.f, tsm2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < kGnFinThreads / 32; ++w) {  // fixed order: bit-reproducible
+    tsd += s_red[0][w];
+    tsdd += s_red[1][w];
+    tsm2 += s_red[2][w];
+  }
+  const float k = static_cast<float>(entries);
+  const float mean = shift + tsd / k;
+  const float m2 = tsm2 + 128.f * fmaxf(tsdd - tsd * tsd / k, 0.f);
+  const float rstd = rsqrtf(m2 / (128.f * k) + eps);  // biased variance, as torch.nn.GroupNorm
+  for (int c = threadIdx.x; c < cpg; c += kGnFinThreads) {
     const int ch = g * cpg + c;
     const float ga = gamma ? __bfloat162float(gamma[ch]) : 1.f;
     const float be = beta ? __bfloat162float(beta[ch]) : 0.f;
@@ -567,7 +599,7 @@ int st_groupnorm_from_partials_nhwc_bf16(const void* x, void* y, const void* gam
   const GnGeom g = gn_geometry(N, HW, C, groups);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* scale_shift = static_cast<float*>(workspace);  // N * C * 2 floats (st_groupnorm_workspace_bytes covers it)
-  launch_kernel(gn_finalize_kernel, dim3((groups + 3) / 4, N), dim3(128), 0, s, static_cast<const float*>(part_a), C_a,
+  launch_kernel(gn_finalize_kernel, dim3(groups, N), dim3(kGnFinThreads), 0, s, static_cast<const float*>(part_a), C_a,
                 static_cast<const float*>(part_b), C_b, static_cast<const __nv_bfloat16*>(gamma),
                 static_cast<const __nv_bfloat16*>(beta), scale_shift, HW / 128, C, groups, g.cpg, eps);
   ST_CHECK_LAUNCH("gn_finalize_kernel");

@@ -354,8 +354,8 @@ def test_groupnorm_of_a_concatenation_uses_both_producers_partials(K):
         K.groupnorm_wrapper(x, 32, gw, gb, 1e-5, True, partials=(pa,))  # partials do not cover all channels
 
 
-def test_groupnorm_large_batch_is_processed_in_l2_sized_rounds(K):
-    """N = 16 at (320, 128^2) is 168 MB: statistics + apply run per group of images that fits the L2 window."""
+def test_groupnorm_large_batch(K):
+    """N = 16 at (320, 128^2): 168 MB, more than the L2 holds."""
     x = (rnd(16, 320, 128, 128, seed=5) + 0.5).cuda().contiguous(memory_format=torch.channels_last)
     w, b = (rnd(320, seed=2) * 0.1 + 1.0).cuda(), (rnd(320, seed=3) * 0.1).cuda()
     got = K.groupnorm_wrapper(x, 32, w, b, 1e-5, True)
@@ -433,3 +433,56 @@ def test_outputs_do_not_overrun_and_repeat_bit_for_bit(K):
     guarded(lambda: K.groupnorm_wrapper(xn, 32, gw, gb, 1e-5, True))
     xl = rnd(77, 640, seed=20).cuda()
     guarded(lambda: K.layer_norm(xl, rnd(640, seed=21).cuda(), rnd(640, seed=22).cuda(), 1e-5))
+
+
+# ---- tile shapes of round 2: 160-wide tiles (32-column tail group) and CTA pairs (cta_group::2) -----------------------
+@pytest.mark.parametrize("m,k,n,block_n", [
+    (2048, 1280, 1280, 160), (2048, 1280, 1280, -160), (2048, 5120, 1280, -160), (2048, 1280, 1280, -192),
+    (2048, 1280, 3840, -256), (400, 192, 328, 160), (400, 192, 328, -160), (512, 64, 200, -160), (8192, 640, 640, -160)])
+def test_linear_tile_shapes_and_cta_pairs(K, m, k, n, block_n):
+    """block_n > 0 forces the tile width, block_n < 0 a CTA-pair launch (two CTAs share one 256 x |block_n| tcgen05
+    tile, each staging half of the weight tile).  Same result, bit for bit, as the launcher's own choice -- the K loop
+    order per output element does not depend on the tile shape -- and the GroupNorm partials ride along."""
+    x, w, b = rnd(m, k, seed=90), rnd(n, k, scale=k ** -0.5, seed=91), rnd(n, seed=92) * 0.1
+    r = rnd(m, n, seed=93)
+    ref = F.linear(x.float(), w.float(), b.float()) + r.float()
+    auto = K.linear(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda(), block_n=128)
+    got = K.linear(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda(), block_n=block_n)
+    check(got.cpu(), ref)
+    assert torch.equal(got, auto)
+    if m % 128 == 0:
+        y, part = K.linear(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda(), block_n=block_n, gn_stats=128)
+        assert torch.equal(y, got)
+        _check_partials(part, y.float())
+
+
+@pytest.mark.parametrize("m,k,n,block_n", [(2048, 1280, 10240, -256), (8192, 640, 5120, -256), (256, 128, 512, -256)])
+def test_geglu_cta_pairs(K, m, k, n, block_n):
+    x, w, b = rnd(m, k, seed=94), rnd(n, k, scale=k ** -0.5, seed=95), rnd(n, seed=96) * 0.1
+    got = K.linear(x.cuda(), w.cuda(), b.cuda(), geglu=True, block_n=block_n)
+    plain = K.linear(x.cuda(), w.cuda(), b.cuda(), geglu=True, block_n=128)
+    assert torch.equal(got, plain)
+    s, g = F.linear(x.float(), w.float(), b.float()).chunk(2, dim=-1)
+    check(got.cpu(), s * F.gelu(g))
+
+
+@pytest.mark.parametrize("n,c,k,hw,block_n", [(2, 320, 320, 128, -160), (2, 640, 640, 64, -160), (2, 1280, 1280, 32, -160),
+                                              (2, 320, 320, 128, -256), (2, 640, 320, 128, 160), (4, 64, 64, 8, -160)])
+def test_conv_tile_shapes_and_cta_pairs(K, n, c, k, hw, block_n):
+    x, w, b = rnd(n, c, hw, hw, seed=21), rnd(k, c, 3, 3, scale=(9 * c) ** -0.5, seed=22), rnd(k, seed=23) * 0.1
+    temb = rnd(n, k, seed=24).cuda()
+    xg = x.cuda().contiguous(memory_format=torch.channels_last)
+    plain = K.conv2d(xg, w.cuda(), b.cuda(), temb=temb, block_n=128)
+    got, part = K.conv2d(xg, w.cuda(), b.cuda(), temb=temb, block_n=block_n, gn_stats=True)
+    assert torch.equal(got, plain)
+    check(got.cpu(), F.conv2d(x.float(), w.float(), b.float(), padding=1) + temb.float().cpu()[:, :, None, None])
+    if part is not None:
+        _check_partials(part, got.permute(0, 2, 3, 1).reshape(-1, k).float())
+
+
+def test_launcher_tile_choice_is_reported(K):
+    """st_debug_choose_tile: what the cost model picks (negative = CTA pair); the big multi-wave GEMMs must be paired."""
+    from stabletriton_b200 import _cabi
+    f = _cabi._load().st_debug_choose_tile
+    f.restype = __import__("ctypes").c_int
+    assert f(2048, 5120, 1, 1280) == -256 and f(8192, 8192, 0, 8192) == -256
