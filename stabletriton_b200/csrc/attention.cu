@@ -322,15 +322,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // the two-CTA kernel above spends ~2.7 k cycles per block and SM because each CTA's MMA -> max -> exp -> MMA
 // chain is serial (single S / P buffers in 256 columns) and both CTAs hit the MUFU phase together.
 constexpr int kA3Stages = 4;
-constexpr int kA3Threads = 480;
-constexpr int kA3SmemBytes = kAttnTileBytes * (1 + 2 * kA3Stages) + 256 + 2048 + 1024;
+// kParts exp warps per TMEM lane quadrant, each owning 128 / kParts score columns of every row.  2: the round-1 layout
+// (480 threads, two 32-column chunks per warp and block, next block's first chunk prefetched).  4: 16 exp warps (736
+// threads, <= 88 registers), one 32-column chunk per warp and block -- four instruction streams per scheduler instead
+// of two to cover the TMEM / barrier latencies that leave the MUFU pipe half idle (ncu: pipe_xu 49 %).
+template <int kParts>
+struct A3Layout {
+  static constexpr int kExpWarps = 4 * kParts;
+  static constexpr int kMaxWarp0 = 2 + kExpWarps;   // 4 max warps
+  static constexpr int kSWarp = kMaxWarp0 + 4;      // S = Q K^T issuer
+  static constexpr int kThreads = 32 * (kSWarp + 1);
+};
+constexpr int kA3Threads = A3Layout<2>::kThreads;   // 480
+constexpr int kA3SmemBytes = kAttnTileBytes * (1 + 2 * kA3Stages) + 256 + 4096 + 1024;
 constexpr int kA3TmemCols = 512;
 constexpr float kA3Tau = 8.f;  // log2 units
 
-template <bool kTrace>
-__global__ void __launch_bounds__(kA3Threads, 1)
+template <bool kTrace, int kParts = 2>
+__global__ void __launch_bounds__(A3Layout<kParts>::kThreads, 1)
 attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using L = A3Layout<kParts>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQ = smem;
@@ -350,7 +362,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   uint64_t* p_free = s_free + 2;           // [3]  P(i).V(i) has drained P buffer i % 3
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 3);
   float* s_m = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 buffers][128 rows] references
-  float* s_l = s_m + 256;                                                         // [2 halves][128 rows] row sums
+  float* s_l = s_m + 256;                                                         // [kParts][128 rows] row sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -375,10 +387,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       mbar_init(&s_full[i], 1);
       mbar_init(&m_ready[i], 128);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 256);
+      mbar_init(&s_free[i], 128 * kParts);
     }
     for (int i = 0; i < 3; ++i) {
-      mbar_init(&p_full[i], 256);
+      mbar_init(&p_full[i], 128 * kParts);
       mbar_init(&p_free[i], 1);
     }
     mbar_fence_init();
@@ -413,7 +425,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         tma_load_4d(sV + st * kAttnTileBytes, &tmap_v, &v_full[st], 0, j * kAttnBlockKV, h, b);
       }
     }
-  } else if (warp == 1 || warp == 14) {
+  } else if (warp == 1 || warp == L::kSWarp) {
     // ===================================== MMA issuers ======================================
     // Two issuing warps on different SM sub-partitions: warp 14 the S = Q K^T products (4 MMAs per block), warp 1 the
     // O += P V products (8 per block).  A single issuer (~250 instructions per block, all on one scheduler) made the
@@ -421,7 +433,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, kAttnBlockKV, 0, 0);  // Q (K-major) x K (K-major)
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);        // P (TMEM)    x V (MN-major)
     constexpr uint32_t kTileStep = kAttnTileBytes >> 4;
-    if (warp == 14) {
+    if (warp == L::kSWarp) {
       const uint64_t desc_q = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
       const uint64_t desc_k0 = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
       auto issue_s = [&](int j) {
@@ -465,7 +477,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         if (j == 2 && lane == 0) AT_TRACE(9);
       }
     }
-  } else if (warp >= 10) {  // 10..13
+  } else if (warp >= L::kMaxWarp0) {  // four warps, one per TMEM lane quadrant
     // ===================================== max warps ========================================
     float m = -INFINITY;  // reference of my row (scaled scores, log2 domain)
     for (int j = 0; j < nkv; ++j) {
@@ -480,7 +492,12 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       uint32_t v[64];
 #pragma unroll
       for (int c = 0; c < 128; c += 64) {
-        tmem_ld_32x32b_x64(t_s + c, v);
+        if (kParts == 4) {  // 736 threads leave 80 registers: a single 64-register load does not fit next to its context
+          tmem_ld_32x32b_x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(v));
+          tmem_ld_32x32b_x32(t_s + c + 32, *reinterpret_cast<uint32_t(*)[32]>(v + 32));
+        } else {
+          tmem_ld_32x32b_x64(t_s + c, v);
+        }
         tmem_ld_wait();
         if (c + 64 > valid) {
 #pragma unroll
@@ -524,10 +541,83 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       // the parity wait cannot alias)
       if (j >= 3) mbar_wait(&p_free[j % 3], (j / 3 - 1) & 1);
       tc_fence_before();
-      if (j == 2 && warp == 10 && lane == 0) AT_TRACE(12);
-      if ((j == 16 || j == 17) && lane == 0) AT_TRACE(16 * (j - 15) + 8 + warp - 10);
-      if (j == 3 && warp == 10 && lane == 0) AT_TRACE(13);
+      if (j == 2 && warp == L::kMaxWarp0 && lane == 0) AT_TRACE(12);
+      if (kParts == 2 && (j == 16 || j == 17) && lane == 0) AT_TRACE(16 * (j - 15) + 8 + warp - L::kMaxWarp0);
+      if (j == 3 && warp == L::kMaxWarp0 && lane == 0) AT_TRACE(13);
       mbar_arrive(&m_ready[buf]);  // release: the exp warps' wait acquires s_m and orders the O rescale before P(j)
+    }
+  } else if (kParts == 4) {
+    // ===================================== exp warps, 4 per quadrant ========================
+    // One 32-column chunk of S(j) per warp and block: wait for the row references, pull the chunk out of TMEM, release
+    // the S buffer, 32 exponentials back to back, sums + bf16 packs, P back into TMEM, publish.  No software prefetch
+    // of the next block (<= 88 registers at 736 threads): the three sibling warps on the scheduler cover the latencies.
+    const int part = (warp - 2) >> 2;            // columns [32 * part, 32 * part + 32) of every block
+    const uint32_t quad_bar = 1 + quad;          // named barrier of this quadrant's four exp warps
+    float m_prev = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int buf = j & 1;
+      const int valid = p.Tk - j * kAttnBlockKV - part * 32;  // my columns >= valid are padding
+      uint32_t cur[32];
+      mbar_wait(&m_ready[buf], (j >> 1) & 1);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(tmem_S + buf * 128 + lane_off + part * 32, cur);
+      const float m = s_m[buf * 128 + row];
+      if (m != m_prev) {
+        l *= ex2_approx(m_prev - m);  // first block: l = 0 and 2^(-inf) = 0
+        m_prev = m;
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[buf]);  // my share of S(j) is in registers: S(j+2) may overwrite the buffer
+      if (valid < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= valid) cur[i] = 0xff800000u;  // -inf -> 2^(-inf) = 0
+      }
+      float e[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) e[i] = ex2_approx_ordered(fmaf(__uint_as_float(cur[i]), p.scale_log2, -m));
+      ready16(e, 0);
+      ready16(e, 16);
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        rs0 += e[i + 0];
+        rs1 += e[i + 1];
+        rs2 += e[i + 2];
+        rs3 += e[i + 3];
+        pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
+        pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
+      }
+      l += (rs0 + rs1) + (rs2 + rs3);
+      tmem_st_32x32b_x16(tmem_P + (j % 3) * 64 + lane_off + part * 16, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[j % 3]);
+    }
+    {
+      mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+      tc_fence_after();
+      s_l[part * 128 + row] = l;
+      asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+      const float inv = 1.f / ((s_l[row] + s_l[128 + row]) + (s_l[256 + row] + s_l[384 + row]));
+      uint32_t o[16];
+      tmem_ld_32x32b_x16(tmem_O + lane_off + part * 16, o);
+      tmem_ld_wait();
+      if (q0 + row < p.Tq) {
+        __nv_bfloat16* orow =
+            p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st + part * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          uint4 ov;
+          ov.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+          ov.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          ov.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          ov.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + i) = ov;
+        }
+      }
     }
   } else {
     // ===================================== exp warps ========================================
@@ -708,6 +798,8 @@ static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int 
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static unsigned long long* g_attn_trace = nullptr;
+constexpr int kAttnDefaultParts = 2;
+static int g_attn_parts = 0;  // 0: not decided yet (ST_ATTN_PARTS or the default)
 
 }  // namespace st
 
@@ -751,6 +843,8 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
     e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
@@ -775,7 +869,16 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   }();
   const bool pipelined = force ? force == 2 : Tk > kAttnBlockKV;
   const bool trace = p.trace != nullptr;  // the phase stamps are compiled out of the production instantiations
-  if (pipelined) {
+  if (g_attn_parts == 0) {
+    const char* e = getenv("ST_ATTN_PARTS");  // exp warps per TMEM lane quadrant: 2 or 4
+    g_attn_parts = (e && e[0] == '4') ? 4 : ((e && e[0] == '2') ? 2 : kAttnDefaultParts);
+  }
+  const int parts = g_attn_parts;
+  if (pipelined && parts == 4 && !trace) {
+    launch_kernel(attn_fwd_pipelined_kernel<false, 4>, dim3(grid), dim3(A3Layout<4>::kThreads), kA3SmemBytes,
+                  static_cast<cudaStream_t>(stream), tq, tk, tv, p);
+    ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
+  } else if (pipelined) {
     launch_kernel(trace ? attn_fwd_pipelined_kernel<true> : attn_fwd_pipelined_kernel<false>, dim3(grid),
                   dim3(kA3Threads), kA3SmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
@@ -788,6 +891,9 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
 }
 
 void st_debug_set_attention_trace(void* buf) { st::g_attn_trace = static_cast<unsigned long long*>(buf); }
+
+// Debug / tuning hook: exp warps per TMEM lane quadrant of the pipelined kernel (2 or 4; 0 = back to the default).
+void st_debug_set_attention_parts(int parts) { st::g_attn_parts = (parts == 2 || parts == 4) ? parts : 0; }
 
 // Debug hook: resident CTAs per SM the driver grants the attention kernel (2 expected).
 int st_debug_attention_occupancy(void) {

@@ -35,20 +35,38 @@ struct TileChoice {
   bool pair;
 };
 
+// Cycle model of one launch, calibrated on B200 (profiles/r02_gemm_tiles.txt):
+//   k-block, one CTA per tile : max(tensor pipe 2*bn, fill/92 B/clk into one SM, fill * CTAs / 11.2 KB/clk out of L2)
+//        (128x256 @148 CTAs 627-664 measured / 634 model, 128x256 @80 520-554 / 521, 128x192 @112 406-470 / 435)
+//   k-block, CTA pair         : max(tensor pipe 2*bn, 2850 / stages) -- a pair stages half the weight tile per CTA, so
+//        the fill never binds, but one trip round its operand ring (MMA commit -> both producers -> TMA -> leader's
+//        barrier) takes ~2850 cycles: 256x256 (6 stages) 536 measured / 512 model, 256x160 and 256x192 (7) 407 / 407
+//   per launch                : set-up until the first operands have landed 2.9 k (pair 4.4 k: cluster scheduling, pair
+//        TMEM allocation, two cluster barriers), the last tile's epilogue ~0.9 k + 1.1 k per 64-column group (GEGLU 2.5 k),
+//        and per further tile max(main loop, epilogue): short-K tiles are epilogue-bound.
 static double tile_cost(int M, int n_cols, bool geglu, int K, int bn, bool pair, int sms) {
   const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
   const int out_cols = geglu ? bn / 2 : bn;
   const int nb = (n_cols + out_cols - 1) / out_cols;
   const long tiles = (long)mb * nb;
-  const long waves = (tiles + sms - 1) / sms;
-  const double ctas = tiles < sms ? (double)tiles : (double)sms;
-  const double l2_bytes = 128.0 * 128.0 + (pair ? 64.0 : 128.0) * bn;  // per CTA and k-block, out of L2
-  const double fill_l2 = l2_bytes / (9600.0 / ctas);
-  const double fill_sm = l2_bytes / 88.0;
-  const double fill = fill_l2 > fill_sm ? fill_l2 : fill_sm;
-  const double mma = 2.0 * bn;
-  const double per_tile = (fill > mma ? fill : mma) * (K / 64) + 1500.0 + 10.0 * out_cols;
-  return waves * per_tile + (pair ? 1500.0 : 0.0);
+  const long slots = pair ? (sms / 2) * 2 : sms;
+  const long waves = (tiles + slots - 1) / slots;
+  const double ctas = tiles < slots ? (double)tiles : (double)slots;
+  double kb;
+  if (pair) {
+    const int stages = bn == 256 ? 6 : 7;
+    kb = 2850.0 / stages;
+  } else {
+    const double bytes = (128.0 + bn) * 128.0;
+    const double fill_sm = bytes / 92.0, fill_l2 = bytes * ctas / 11200.0;
+    kb = fill_sm > fill_l2 ? fill_sm : fill_l2;
+  }
+  if (kb < 2.0 * bn) kb = 2.0 * bn;
+  const double main_loop = kb * (K / 64);
+  const double groups = (out_cols + 63) / 64;
+  const double epilogue = 900.0 + (geglu ? 2500.0 : 1100.0) * groups;
+  const double steady = main_loop > epilogue ? main_loop : epilogue;
+  return (pair ? 4400.0 : 2900.0) + main_loop + (waves - 1) * steady + epilogue;
 }
 
 static TileChoice choose_tile(int M, int n_cols, bool geglu, int K, bool allow_pair) {
@@ -65,7 +83,6 @@ static TileChoice choose_tile(int M, int n_cols, bool geglu, int K, bool allow_p
     for (int pair = 0; pair < 2; ++pair) {
       if (pair && (policy == 0 || !pair_possible(M, bn, geglu))) continue;
       if (!pair && policy == 1 && pair_possible(M, bn, geglu)) continue;
-      if (!pair && bn == 160) continue;  // 160 only pays as a pair tile (un-paired it is fill-bound like 192)
       const double cost = tile_cost(M, n_cols, geglu, K, bn, pair != 0, sms);
       if (cost < best_cost * 0.97) {  // ties go to the narrower / un-paired tile
         best_cost = cost;

@@ -486,3 +486,25 @@ def test_launcher_tile_choice_is_reported(K):
     f = _cabi._load().st_debug_choose_tile
     f.restype = __import__("ctypes").c_int
     assert f(2048, 5120, 1, 1280) == -256 and f(8192, 8192, 0, 8192) == -256
+
+
+@pytest.mark.parametrize("b,h,tq,tk", [(2, 10, 4096, 4096), (2, 20, 1024, 1024), (1, 2, 300, 1000), (1, 3, 129, 129)])
+def test_attention_four_exp_warps_per_quadrant(K, b, h, tq, tk):
+    """The 736-thread layout of the pipelined kernel (16 exp warps, one 32-column chunk each) against the oracle and
+    against the 480-thread layout: both evaluate the same per-element arithmetic, so P and the row sums -- hence the
+    output -- must agree to the last bit."""
+    from stabletriton_b200 import _cabi
+    L = _cabi._load()
+    q, k, v = rnd(b, tq, h * 64, seed=40), rnd(b, tk, h * 64, seed=41), rnd(b, tk, h * 64, seed=42)
+    ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
+    try:
+        L.st_debug_set_attention_parts(2)
+        two = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+        L.st_debug_set_attention_parts(4)
+        four = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        L.st_debug_set_attention_parts(0)
+    check(four.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
+    rel, cos = parity(four.float(), two.float())
+    assert rel <= 4e-3, (rel, cos)  # the row sum is accumulated in a different order (4 partial sums instead of 2)
