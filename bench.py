@@ -492,14 +492,15 @@ def run_gpu_arm(args):
         roofline = {
             "bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all Linear + conv launches of one step)",
             "traffic_note": "dram read+write bytes per launch, mean over the 495 launches of one step, from the committed "
-                            "ncu capture profiles/r01_ncu_launch_summary_v5.json (ncu flushes L2 before every launch, so "
+                            "ncu capture profiles/r02_ncu_launch_summary_v1.json (ncu flushes L2 before every launch, so "
                             "activations are counted as DRAM reads: 5.1 GB of weights + 6.4 GB of activations per step)",
             "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops_sustained"], "traffic": ncu_gemm_traffic_per_launch(),
             "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "launches_per_step": len(gemm_calls),
             "flops_per_step": fam_flops, "ms_per_step_in_kernel": fam_ms, "share_of_step": fam_ms / ms_step,
-            "whole_step_frac_of_roofline": (FLOPS_CONFIG2 * prompts / peaks["tflops_sustained"] / 1e12
-                                            + 3.754e9 * prompts / peaks["hbm_gbs"] / 1e9) / (ms_step * 1e-3),
+            "whole_step_frac_of_roofline": (latent / 128.0) ** 2 * prompts
+                                           * (FLOPS_CONFIG2 / peaks["tflops_sustained"] / 1e12
+                                              + 3.754e9 / peaks["hbm_gbs"] / 1e9) / (ms_step * 1e-3),
         }
         # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
         cpu = None
@@ -549,7 +550,7 @@ def run_gpu_arm(args):
 
 def ncu_gemm_traffic_per_launch():
     """DRAM bytes per GEMM launch from the committed ncu launch list (profiles/), or None if it is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_launch_summary_v5.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_launch_summary_v1.json")
     try:
         with open(path) as f:
             fam = json.load(f)["families"]["gemm_bf16_tc_kernel"]
