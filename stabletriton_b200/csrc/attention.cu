@@ -301,6 +301,194 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Short-context variant for Tk <= 80 (the 77-token cross attention): one K/V block of 80 rows, everything in one
+// pass, small enough for FOUR resident CTAs per SM -- 37 KB of shared memory, 128 TMEM columns, 160 threads.  The
+// launches of the step are latency chains (TMA -> S -> softmax -> P.V -> store, ~5 us) over 320 CTAs (Tq = 1024) or
+// 640 (Tq = 4096): with the two-CTA-per-SM kernel above (296 slots) the 24-CTA second wave doubled the chain.
+//
+//   warp 0      TMA loads (Q + K on one barrier, V on its own), then the two MMA batches
+//   warps 1-4   one query row per thread: the whole 80-column score row in registers (one TMEM round trip), exact
+//               max, exponentials, bf16 P written over the dead S columns, then O / l -> HBM
+//
+//   TMEM   S [0,80) fp32;  P [0,40) packed bf16, aliasing S (a thread overwrites only columns of its own lane, after
+//          it has read them);  O [64,128) (S is dead by the time P.V is issued)
+constexpr int kShortKV = 80;
+constexpr int kShortThreads = 160;
+constexpr int kShortKVBytes = kShortKV * kAttnD * 2;
+constexpr int kShortSmemBytes = kAttnTileBytes + 2 * kShortKVBytes + 128 + 1024;
+constexpr int kShortTmemCols = 128;
+
+__global__ void __launch_bounds__(kShortThreads, 3)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAttnTileBytes;
+  uint8_t* sV = sK + kShortKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kShortKVBytes);
+  uint64_t* qk_full = bars;
+  uint64_t* v_full = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kAttnBlockQ;
+  const int b = blockIdx.y / p.H;
+  const int h = blockIdx.y - b * p.H;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<kShortTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // prologue above touched only shared / tensor memory
+  pdl_wait();
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_P = tmem_base;
+  const uint32_t tmem_O = tmem_base + 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qk_full, kAttnTileBytes + kShortKVBytes);
+      tma_load_4d(sQ, &tmap_q, qk_full, 0, q0, h, b);
+      tma_load_4d(sK, &tmap_k, qk_full, 0, 0, h, b);
+      mbar_expect_tx(v_full, kShortKVBytes);
+      tma_load_4d(sV, &tmap_v, v_full, 0, 0, h, b);
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, kShortKV, 0, 0);  // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);    // P (TMEM)    x V (MN-major)
+    const uint64_t desc_q = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+    const uint64_t desc_k = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
+    const uint64_t desc_v = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+    mbar_wait(qk_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < kAttnD / 16; ++k) umma_bf16_ss_elect(tmem_S, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
+    umma_commit_elect(s_full);
+    mbar_wait(v_full, 0);
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int kk = 0; kk < kShortKV / 16; ++kk)  // 16 V rows (2 KB) per instruction
+      umma_bf16_ts_elect(tmem_O, tmem_P + kk * 8, desc_v + 128 * kk, idesc_o, kk != 0);
+    umma_commit_elect(o_full);
+  } else {
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int valid = p.Tk;     // score columns >= valid are padding (K rows zero-filled by TMA)
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    uint32_t s0[32], s1[32], s2[16];
+    tmem_ld_32x32b_x32(tmem_S + lane_off, s0);
+    tmem_ld_32x32b_x32(tmem_S + lane_off + 32, s1);
+    tmem_ld_32x32b_x16(tmem_S + lane_off + 64, s2);
+    tmem_ld_wait();
+    if (valid < 64) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i >= valid) s0[i] = 0xff800000u;  // -inf
+        if (32 + i >= valid) s1[i] = 0xff800000u;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (64 + i >= valid) s2[i] = 0xff800000u;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) mx = max3f(mx, __uint_as_float(s0[i]), __uint_as_float(s0[i + 1]));
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) mx = max3f(mx, __uint_as_float(s1[i]), __uint_as_float(s1[i + 1]));
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) mx = max3f(mx, __uint_as_float(s2[i]), __uint_as_float(s2[i + 1]));
+    const float neg_m = -mx * p.scale_log2;  // scale > 0 commutes with max; column 0 is always valid, so mx is finite
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    auto exp_pack = [&](const uint32_t* v, uint32_t* pk, int n) {
+#pragma unroll
+      for (int i = 0; i < n; i += 4) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(v[i + 0]), p.scale_log2, neg_m));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
+        const float e2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), p.scale_log2, neg_m));
+        const float e3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), p.scale_log2, neg_m));
+        l0 += e0;
+        l1 += e1;
+        l2 += e2;
+        l3 += e3;
+        pk[(i >> 1) + 0] = pack_bf16x2(e0, e1);
+        pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
+      }
+    };
+    {
+      uint32_t pk[16];
+      exp_pack(s0, pk, 32);
+      tmem_st_32x32b_x16(tmem_P + lane_off, pk);
+    }
+    {
+      uint32_t pk[16];
+      exp_pack(s1, pk, 32);
+      tmem_st_32x32b_x16(tmem_P + lane_off + 16, pk);
+    }
+    {
+      uint32_t pk[8];
+      exp_pack(s2, pk, 16);
+      tmem_st_32x32b_x8(tmem_P + lane_off + 32, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(p_full);
+    const float inv = 1.f / ((l0 + l1) + (l2 + l3));
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32b_x32(tmem_O + lane_off, o0);
+    tmem_ld_32x32b_x32(tmem_O + lane_off + 32, o1);
+    tmem_ld_wait();
+    if (q0 + row < p.Tq) {
+      __nv_bfloat16* orow = p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(o0[i + 0]) * inv, __uint_as_float(o0[i + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + i) = o;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(o1[i + 0]) * inv, __uint_as_float(o1[i + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + 32 + i) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<kShortTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pipelined variant for Tk > 128 (self-attention): ONE CTA per SM that owns all 512 TMEM columns, so S and P
 // are double-buffered and O accumulates in TMEM across the whole K/V sweep; 480 threads, warp-specialised:
 //
@@ -338,7 +526,14 @@ constexpr int kA3SmemBytes = kAttnTileBytes * (1 + 2 * kA3Stages) + 256 + 4096 +
 constexpr int kA3TmemCols = 512;
 constexpr float kA3Tau = 8.f;  // log2 units
 
-template <bool kTrace, int kParts = 2>
+// kPoly: of every 8 element pairs an exp warp (kParts == 2 layout) processes, kPoly take the FMA-pipe polynomial
+// (ex2_poly2, ptx.cuh) instead of MUFU.EX2; the pairs are spread evenly (Bresenham) so the polynomial's FMA-pipe work
+// issues in the shadow of the MUFU stream.  Measured (profiles/r02_attention_experiments.txt): moving 12.5 - 37.5 % of
+// the exponentials off the MUFU pipe changes nothing (T = 4096: 144 us either way), 50 % is slower -- the block period
+// (~1.45 k cycles) is not set by MUFU throughput.  Opt-in (ST_ATTN_POLY=2); the default instantiation has kPoly = 0.
+__host__ __device__ constexpr bool a3_is_poly_pair(int q, int poly) { return ((q % 8 + 1) * poly) / 8 != ((q % 8) * poly) / 8; }
+
+template <bool kTrace, int kParts = 2, int kPoly = 0>
 __global__ void __launch_bounds__(A3Layout<kParts>::kThreads, 1)
 attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -687,27 +882,45 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         // behind their MUFUs (what the compiler does on its own) the in-order warp waits out the MUFU latency for
         // every pair -- 22 cycles per element, independent of what the sibling warp does (measured).
         float e[32];
+        {
+          // t = s * c - m for all 32 columns (FFMA2: one issue slot per pair)
+          const float neg_m = -m;
+          float t[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) e[i] = ex2_approx_ordered(fmaf(__uint_as_float(cur[i]), p.scale_log2, -m));
-        if (c == 0) {
-          // the second chunk has landed by now: all of my S(j) is in registers, and the sooner the MMA warp may
-          // overwrite this S buffer with S(j+2), the sooner the max warps get to publish m(j+2)
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&s_free[buf]);
+          for (int q = 0; q < 16; ++q)
+            fma2_bcast(__uint_as_float(cur[2 * q]), __uint_as_float(cur[2 * q + 1]), p.scale_log2, neg_m, t[2 * q], t[2 * q + 1]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (!a3_is_poly_pair(q, kPoly)) {
+              e[2 * q] = ex2_approx_ordered(t[2 * q]);
+              e[2 * q + 1] = ex2_approx_ordered(t[2 * q + 1]);
+            }
+          if (c == 0) {
+            // the second chunk has landed by now: all of my S(j) is in registers, and the sooner the MMA warp may
+            // overwrite this S buffer with S(j+2), the sooner the max warps get to publish m(j+2)
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&s_free[buf]);
+          }
+#pragma unroll
+          for (int q = 8; q < 16; ++q)
+            if (!a3_is_poly_pair(q, kPoly)) {
+              e[2 * q] = ex2_approx_ordered(t[2 * q]);
+              e[2 * q + 1] = ex2_approx_ordered(t[2 * q + 1]);
+            }
+          // the polynomial pairs: plain (non-volatile) FMA-pipe code, free to be scheduled between the MUFUs above
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (a3_is_poly_pair(q, kPoly)) ex2_poly2(t[2 * q], t[2 * q + 1], e[2 * q], e[2 * q + 1]);
         }
-#pragma unroll
-        for (int i = 16; i < 32; ++i) e[i] = ex2_approx_ordered(fmaf(__uint_as_float(cur[i]), p.scale_log2, -m));
         ready16(e, 0);
         ready16(e, 16);
         if (tr) AT_TRACE(c == 0 ? 50 : 55);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          rs0 += e[i + 0];
-          rs1 += e[i + 1];
-          rs2 += e[i + 2];
-          rs3 += e[i + 3];
+          add2_acc(rs0, rs1, e[i + 0], e[i + 1]);
+          add2_acc(rs2, rs3, e[i + 2], e[i + 3]);
           pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
           pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
         }
@@ -766,7 +979,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 // box = [1, 1, 128, 64].  Covers both (B, T, H*64) activations (sh = 64, st = row pitch) and the
 // reference's (B, H, T, D) layout (kernels/attention_fa2.py:113-140).  OOB rows (t >= T) read as zero.
 static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int T, long long sb, long long sh,
-                          long long st_) {
+                          long long st_, int box_rows = 128) {
   typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -783,7 +996,7 @@ static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int 
   }
   cuuint64_t dims[4] = {64, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)st_ * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
-  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -800,6 +1013,8 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static unsigned long long* g_attn_trace = nullptr;
 constexpr int kAttnDefaultParts = 2;
 static int g_attn_parts = 0;  // 0: not decided yet (ST_ATTN_PARTS or the default)
+constexpr int kAttnDefaultPoly = 0;
+static int g_attn_poly = -1;  // -1: not decided yet (ST_ATTN_POLY or the default)
 
 }  // namespace st
 
@@ -821,9 +1036,18 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_bhtd(&tq, q, B, H, Tq, q_sb, q_sh, q_st);
   if (rc != ST_OK) return rc;
-  rc = make_tmap_bhtd(&tk, k, B, H, Tk, k_sb, k_sh, k_st);
+  // one K/V block (cross-attention, Tk = 77): the short-context kernel (Tk <= 80) or the two-CTA-per-SM kernel
+  // (Tk <= 128); longer sweeps: the pipelined one
+  static const int force = [] {
+    const char* e = getenv("ST_ATTN_IMPL");  // debug: "2cta" / "pipelined" / "short"
+    return !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : (!strcmp(e, "short") ? 3 : 0)));
+  }();
+  const bool pipelined = (force == 1 || force == 2) ? force == 2 : Tk > kAttnBlockKV;
+  const bool short_kv = !pipelined && Tk <= kShortKV && force != 1;
+  const int kv_box = short_kv ? kShortKV : kAttnBlockKV;
+  rc = make_tmap_bhtd(&tk, k, B, H, Tk, k_sb, k_sh, k_st, kv_box);
   if (rc != ST_OK) return rc;
-  rc = make_tmap_bhtd(&tv, v, B, H, Tk, v_sb, v_sh, v_st);
+  rc = make_tmap_bhtd(&tv, v, B, H, Tk, v_sb, v_sh, v_st, kv_box);
   if (rc != ST_OK) return rc;
   static PerDeviceOnce configured;  // function attributes are per context: once per device, not per process
   const int dev = current_device();
@@ -840,11 +1064,14 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
                          cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(attn_fwd_short_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
@@ -862,12 +1089,6 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
   const dim3 grid((Tq + kAttnBlockQ - 1) / kAttnBlockQ, B * H);
-  // one K/V block (cross-attention, Tk = 77): the two-CTA-per-SM kernel; longer sweeps: the pipelined one
-  static const int force = [] {
-    const char* e = getenv("ST_ATTN_IMPL");  // debug: "2cta" / "pipelined"
-    return !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : 0));
-  }();
-  const bool pipelined = force ? force == 2 : Tk > kAttnBlockKV;
   const bool trace = p.trace != nullptr;  // the phase stamps are compiled out of the production instantiations
   if (g_attn_parts == 0) {
     const char* e = getenv("ST_ATTN_PARTS");  // exp warps per TMEM lane quadrant: 2 or 4
@@ -879,9 +1100,22 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
                   static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
   } else if (pipelined) {
-    launch_kernel(trace ? attn_fwd_pipelined_kernel<true> : attn_fwd_pipelined_kernel<false>, dim3(grid),
-                  dim3(kA3Threads), kA3SmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
+    if (g_attn_poly < 0) {
+      const char* e = getenv("ST_ATTN_POLY");  // polynomial pairs out of every 8: 0 or 2 (a quarter of the exponentials)
+      g_attn_poly = (e && e[0] == '2') ? 2 : ((e && e[0] == '0') ? 0 : kAttnDefaultPoly);
+    }
+    auto fn = attn_fwd_pipelined_kernel<false, 2, 0>;
+    switch (trace ? -1 : g_attn_poly) {
+      case -1: fn = attn_fwd_pipelined_kernel<true>; break;
+      case 2: fn = attn_fwd_pipelined_kernel<false, 2, 2>; break;
+      default: break;
+    }
+    launch_kernel(fn, dim3(grid), dim3(kA3Threads), kA3SmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
+  } else if (short_kv) {
+    launch_kernel(attn_fwd_short_kernel, dim3(grid), dim3(kShortThreads), kShortSmemBytes, static_cast<cudaStream_t>(stream),
+                  tq, tk, tv, p);
+    ST_CHECK_LAUNCH("attn_fwd_short_kernel");
   } else {
     launch_kernel(trace ? attn_fwd_kernel<true> : attn_fwd_kernel<false>, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes,
                   static_cast<cudaStream_t>(stream), tq, tk, tv, p);
@@ -894,6 +1128,9 @@ void st_debug_set_attention_trace(void* buf) { st::g_attn_trace = static_cast<un
 
 // Debug / tuning hook: exp warps per TMEM lane quadrant of the pipelined kernel (2 or 4; 0 = back to the default).
 void st_debug_set_attention_parts(int parts) { st::g_attn_parts = (parts == 2 || parts == 4) ? parts : 0; }
+
+// Debug / tuning hook: element pairs out of every 8 whose exponential takes the FMA-pipe polynomial (0 or 2; -1 = default).
+void st_debug_set_attention_poly(int pairs) { st::g_attn_poly = (pairs == 0 || pairs == 2) ? pairs : -1; }
 
 // Debug hook: resident CTAs per SM the driver grants the attention kernel (2 expected).
 int st_debug_attention_occupancy(void) {

@@ -426,6 +426,64 @@ __device__ __forceinline__ float ex2_approx_ordered(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (FFMA2 / FADD2, sm_100+): one issue slot for two elements.
+// (y0, y1) = (x0, x1) * a + b
+__device__ __forceinline__ void fma2_bcast(float x0, float x1, float a, float b, float& y0, float& y1) {
+  asm("{\n"
+      ".reg .b64 x, a, b, y;\n"
+      "mov.b64 x, {%2, %3};\n"
+      "mov.b64 a, {%4, %4};\n"
+      "mov.b64 b, {%5, %5};\n"
+      "fma.rn.ftz.f32x2 y, x, a, b;\n"
+      "mov.b64 {%0, %1}, y;\n"
+      "}\n"
+      : "=f"(y0), "=f"(y1)
+      : "f"(x0), "f"(x1), "f"(a), "f"(b));
+}
+// (a0, a1) += (b0, b1)
+__device__ __forceinline__ void add2_acc(float& a0, float& a1, float b0, float b1) {
+  asm("{\n"
+      ".reg .b64 a, b;\n"
+      "mov.b64 a, {%0, %1};\n"
+      "mov.b64 b, {%2, %3};\n"
+      "add.rn.ftz.f32x2 a, a, b;\n"
+      "mov.b64 {%0, %1}, a;\n"
+      "}\n"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+// 2^x for two elements on the FMA pipe, no MUFU (x <= 127; x below -125 is clamped, the result is then ~2^-125):
+// Cody-Waite split x = n + f with f in [0, 1) (add with round-down to the 1.5 * 2^23 magic constant leaves n in the low
+// mantissa bits), degree-3 minimax polynomial for 2^f (max relative error 9e-5: a 45th of the bf16 rounding the result
+// goes through), n shifted into the exponent field.  5 issue slots per element against 8 MUFU-pipe cycles: the softmax
+// of the self-attention kernel routes a fraction of its exponentials here because the MUFU pipe (16 / clk / SM) is
+// its floor (1024 cycles per 128 x 128 block against 512 of tensor pipe).
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& y0, float& y1) {
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  uint32_t r0, r1, p0, p1;
+  asm("{\n"
+      ".reg .b64 x, r, n, f, p, mg, c3, c2, c1, c0;\n"
+      "mov.b64 x, {%4, %5};\n"
+      "mov.b64 mg, {%6, %6};\n"
+      "mov.b64 c3, {%7, %7};\n"
+      "mov.b64 c2, {%8, %8};\n"
+      "mov.b64 c1, {%9, %9};\n"
+      "mov.b64 c0, {%10, %10};\n"
+      "add.rm.ftz.f32x2 r, x, mg;\n"
+      "sub.rn.ftz.f32x2 n, r, mg;\n"
+      "sub.rn.ftz.f32x2 f, x, n;\n"
+      "fma.rn.ftz.f32x2 p, c3, f, c2;\n"
+      "fma.rn.ftz.f32x2 p, p, f, c1;\n"
+      "fma.rn.ftz.f32x2 p, p, f, c0;\n"
+      "mov.b64 {%0, %1}, r;\n"
+      "mov.b64 {%2, %3}, p;\n"
+      "}\n"
+      : "=r"(r0), "=r"(r1), "=r"(p0), "=r"(p1)
+      : "f"(x0), "f"(x1), "f"(12582912.f), "f"(0.0771190897f), "f"(0.2275643945f), "f"(0.6951461434f), "f"(1.0f));
+  y0 = __uint_as_float(p0 + (r0 << 23));
+  y1 = __uint_as_float(p1 + (r1 << 23));
+}
 // scheduling fence for 16 registers: everything that consumes them is issued after everything that produced them
 __device__ __forceinline__ void ready16(float (&e)[32], int o) {
   asm volatile("" : "+f"(e[o + 0]), "+f"(e[o + 1]), "+f"(e[o + 2]), "+f"(e[o + 3]), "+f"(e[o + 4]), "+f"(e[o + 5]),

@@ -150,7 +150,11 @@ def test_linear_geglu_fused_epilogue(K, m, k, n):
 
 
 @pytest.mark.parametrize("b,h,tq,tk", [(2, 10, 4096, 4096), (2, 20, 1024, 1024), (2, 10, 4096, 77), (2, 20, 1024, 77),
-                                        (1, 3, 200, 333), (1, 1, 1, 77)])
+                                        (1, 3, 200, 333), (1, 1, 1, 77),
+                                        # short-context kernel (Tk <= 80): full box, exactly 64, ragged, a single key
+                                        (1, 2, 300, 80), (1, 2, 130, 64), (2, 3, 128, 17), (1, 1, 77, 1),
+                                        # one-block two-CTA kernel (80 < Tk <= 128)
+                                        (1, 2, 200, 100), (1, 2, 256, 128), (1, 2, 100, 81)])
 def test_attention(K, b, h, tq, tk):
     q, k, v = rnd(b, tq, h * 64, seed=18), rnd(b, tk, h * 64, seed=19), rnd(b, tk, h * 64, seed=20)
     ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
@@ -486,6 +490,27 @@ def test_launcher_tile_choice_is_reported(K):
     f = _cabi._load().st_debug_choose_tile
     f.restype = __import__("ctypes").c_int
     assert f(2048, 5120, 1, 1280) == -256 and f(8192, 8192, 0, 8192) == -256
+
+
+def test_attention_polynomial_exp2_share(K):
+    """ST_ATTN_POLY=2 instantiation of the pipelined kernel: a quarter of the exponentials evaluated by the FMA-pipe
+    polynomial (Cody-Waite split + degree-3 minimax, relative error 9e-5) instead of MUFU.EX2 -- same parity bar."""
+    from stabletriton_b200 import _cabi
+    L = _cabi._load()
+    b, h, tq, tk = 1, 3, 300, 1000
+    q, k, v = rnd(b, tq, h * 64, seed=50) * 2.0, rnd(b, tk, h * 64, seed=51) * 2.0, rnd(b, tk, h * 64, seed=52)
+    ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
+    try:
+        L.st_debug_set_attention_poly(0)
+        base = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+        L.st_debug_set_attention_poly(2)
+        poly = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        L.st_debug_set_attention_poly(-1)
+    check(poly.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
+    rel, cos = parity(poly.float(), base.float())
+    assert rel <= 8e-3 and cos >= 0.99999, (rel, cos)
 
 
 @pytest.mark.parametrize("b,h,tq,tk", [(2, 10, 4096, 4096), (2, 20, 1024, 1024), (1, 2, 300, 1000), (1, 3, 129, 129)])
