@@ -426,29 +426,49 @@ def run_gpu_arm(args):
         one_c = synth.synth_inputs(1, latent, cfg, seed=2024, device=device, dtype=torch.bfloat16)
         one_u = synth.synth_inputs(1, latent, cfg, seed=2025, device=device, dtype=torch.bfloat16)
         as_cond = lambda d: {"encoder_hidden_states": d["encoder_hidden_states"], **d["added_cond_kwargs"]}  # noqa: E731
-        cl = DenoiseLoop(compiled, prompts=1, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device,
-                         cfg_row=rank, hoist_prompt_constants=False)
-        cl.set_conditioning(as_cond(one_c), as_cond(one_u))
-        cl.reset(one_c["sample"].float())
-        cl.capture()
-        cl.reset(one_c["sample"].float())
-        for _ in range(warmup):
-            cl.run_step()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        c0.record()
-        for _ in range(steps):
-            cl.run_step()
-        c1.record()
-        barrier()
-        t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_split = t.item()
-        cfg_split = {"value": steps / (ms_split * 1e-3), "unit": UNIT, "ms_per_step": ms_split / steps, "prompts": 1,
-                     "collective": f"NCCL all_gather_into_tensor of eps per step, 2 x {cfg.out_channels * latent * latent * 2}"
-                                   f" B, captured in the step graph",
+
+        def time_split(exchange):
+            cl = DenoiseLoop(compiled, prompts=1, latent_hw=latent, num_steps=max(steps + warmup, 30), device=device,
+                             cfg_row=rank, hoist_prompt_constants=False, exchange=exchange)
+            cl.set_conditioning(as_cond(one_c), as_cond(one_u))
+            cl.reset(one_c["sample"].float())
+            cl.capture()
+            cl.reset(one_c["sample"].float())
+            for _ in range(warmup):
+                cl.run_step()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            c0.record()
+            for _ in range(steps):
+                cl.run_step()
+            c1.record()
+            barrier()
+            t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            final = cl.x.clone()
+            timed_out = cl.peer.error() if cl.peer is not None else 0
+            if cl.peer is not None:
+                cl.peer.close()
+            return t.item(), final, timed_out
+
+        row_bytes = cfg.out_channels * latent * latent * 2
+        ms_nccl, x_nccl, _ = time_split("nccl")
+        cfg_split = {"value": steps / (ms_nccl * 1e-3), "unit": UNIT, "ms_per_step": ms_nccl / steps, "prompts": 1,
+                     "collective": f"NCCL all_gather_into_tensor of eps per step, 2 x {row_bytes} B, captured in the step "
+                                   f"graph, followed by the Euler kernel",
                      "note": "latency mode: ONE prompt on two GPUs (rank 0 = uncond row, rank 1 = cond row)"}
-        del cl
+        try:  # the fused exchange needs CUDA IPC + P2P between the two GPUs; the NCCL line above stands either way
+            ms_peer, x_peer, timed_out = time_split("peer")
+            ok = torch.tensor([int(torch.equal(x_peer, x_nccl) and timed_out == 0)], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            cfg_split["peer_exchange"] = {
+                "value": steps / (ms_peer * 1e-3), "unit": UNIT, "ms_per_step": ms_peer / steps,
+                "bit_identical_to_nccl_path": bool(ok.item()),
+                "collective": f"none: cfg_exchange_euler_kernel stores each rank's eps row ({row_bytes} B) into the peer "
+                              f"GPU's memory over NVLink (P2P stores + release/acquire.sys flag) and applies the Euler "
+                              f"update in the same launch, captured in the step graph"}
+        except Exception as exc:  # noqa: BLE001 -- reported, not fatal for the headline
+            cfg_split["peer_exchange"] = {"unavailable": repr(exc)[:300]}
 
     # ---- max over ranks -------------------------------------------------------------------------------
     if world > 1:

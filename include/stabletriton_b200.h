@@ -184,6 +184,26 @@ int st_euler_cfg_update(const void* eps_uncond, const void* eps_cond, float* x, 
                         const float* sigmas, const int* step, st_stream_t stream);
 int st_advance_step(int* step, float* t_out, const float* timesteps, st_stream_t stream);
 
+/* ---- 2-GPU CFG split: eps exchange over NVLink peer memory, fused with the Euler update -----------
+ * (one prompt on two GPUs, rank 0 = uncond row, rank 1 = cond row; the reference has no
+ * multi-GPU path.)  Each rank owns an exchange slab of st_peer_slab_bytes(n) bytes obtained from st_peer_alloc
+ * (cudaMalloc, zeroed), exports it with st_peer_export (a 64-byte CUDA IPC handle the host code hands to the other
+ * process, e.g. through torch.distributed) and maps the peer's slab with st_peer_import.
+ *   st_cfg_exchange_euler_update: ONE kernel that stores this rank's eps row (n bf16) into the peer's slab with P2P
+ *   stores, publishes a sequence number there (release.sys), waits for the peer's row in its own slab (acquire.sys)
+ *   and applies x += (sigma[step+1] - sigma[step]) * (eps_u + g (eps_c - eps_u)) to its replica of the latents.
+ *   Capturable; both ranks must launch it the same number of times (slab parity = a device-resident epoch counter).
+ *   A peer that never publishes is given 2 s, then the launch finishes and st_peer_error reports the exchange. */
+size_t st_peer_slab_bytes(long long n);
+int st_peer_alloc(size_t bytes, void** ptr);
+int st_peer_free(void* ptr);
+int st_peer_export(void* ptr, unsigned char* handle64);
+int st_peer_import(const unsigned char* handle64, void** ptr);
+int st_peer_close(void* ptr);
+int st_cfg_exchange_euler_update(const void* eps_local, int row, void* slab_local, void* slab_peer, float* x, long long n,
+                                 float guidance, const float* sigmas, const int* step, st_stream_t stream);
+int st_peer_error(const void* slab_local, unsigned* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,14 @@ PROTOTYPES = {
     "st_scale_model_input": (I, [P, P, LL, I, P, P, P]),
     "st_euler_cfg_update": (I, [P, P, P, LL, F, P, P, P]),
     "st_advance_step": (I, [P, P, P, P]),
+    "st_peer_slab_bytes": (c_size_t, [LL]),
+    "st_peer_alloc": (I, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "st_peer_free": (I, [P]),
+    "st_peer_export": (I, [P, c_char_p]),
+    "st_peer_import": (I, [c_char_p, ctypes.POINTER(c_void_p)]),
+    "st_peer_close": (I, [P]),
+    "st_cfg_exchange_euler_update": (I, [P, I, P, P, P, LL, F, P, P, P]),
+    "st_peer_error": (I, [P, ctypes.POINTER(c_uint)]),
 }
 
 ST_EPI_SILU = 1
@@ -57,7 +65,8 @@ class StableTritonError(RuntimeError):
 
 
 _NOT_KERNELS = {"st_version", "st_last_error_string", "st_launch_count", "st_reset_launch_count",
-                "st_groupnorm_workspace_bytes", "st_workspace_bytes", "st_set_workspace"}
+                "st_groupnorm_workspace_bytes", "st_workspace_bytes", "st_set_workspace", "st_peer_slab_bytes",
+                "st_peer_alloc", "st_peer_free", "st_peer_export", "st_peer_import", "st_peer_close", "st_peer_error"}
 _recording = None  # list of (symbol, args) while a recording is active
 
 

@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(CSRC, "libstabletriton_b200.so")
 SELFTEST_PATH = os.path.join(CSRC, "selftest")
 
-LIB_SOURCES = ["common.cu", "gemm.cu", "norms.cu", "elementwise.cu", "attention.cu"]
+LIB_SOURCES = ["common.cu", "gemm.cu", "norms.cu", "elementwise.cu", "attention.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

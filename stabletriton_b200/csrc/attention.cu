@@ -42,6 +42,7 @@ struct AttnParams {
   int H, Tq, Tk;
   float scale_log2;
   unsigned long long* trace;  // debug: 16 clock64 stamps for CTA (0,0), or nullptr
+  int ablate;                 // debug (ST_ATTN_ABLATE, timing only -- results are wrong): see attn_fwd_pipelined_kernel<.., kAblate>
 };
 
 // Registers are allocated per group of 4 warps: the 10 warps of this CTA cost as much as 12, so two resident
@@ -533,7 +534,10 @@ constexpr float kA3Tau = 8.f;  // log2 units
 // (~1.45 k cycles) is not set by MUFU throughput.  Opt-in (ST_ATTN_POLY=2); the default instantiation has kPoly = 0.
 __host__ __device__ constexpr bool a3_is_poly_pair(int q, int poly) { return ((q % 8 + 1) * poly) / 8 != ((q % 8) * poly) / 8; }
 
-template <bool kTrace, int kParts = 2, int kPoly = 0>
+// kAblate: timing-only instantiation for bottleneck hunting -- p.ablate bits switch pieces of the pipeline off (1: no MUFU
+// in the exp warps, 2: no tcgen05.st of P, 4: P.V MMAs not issued, 8: max warps do not read S, 16: no row sums / bf16
+// packs, 32: S MMAs not issued).  Results are wrong by construction; never selected unless ST_ATTN_ABLATE is set.
+template <bool kTrace, int kParts = 2, int kPoly = 0, bool kAblate = false>
 __global__ void __launch_bounds__(A3Layout<kParts>::kThreads, 1)
 attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -637,8 +641,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         tc_fence_after();
         const uint64_t dk = desc_k0 + static_cast<uint64_t>(st * kTileStep);
         const uint32_t d = tmem_S + (j & 1) * 128;
+        if (!(kAblate && (p.ablate & 32))) {
 #pragma unroll
-        for (int k = 0; k < kAttnD / 16; ++k) umma_bf16_ss_elect(d, desc_q + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < kAttnD / 16; ++k) umma_bf16_ss_elect(d, desc_q + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        }
         umma_commit_elect(&k_empty[st]);
         umma_commit_elect(&s_full[j & 1]);
       };
@@ -663,9 +669,11 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         tc_fence_after();
         const uint64_t dv = desc_v0 + static_cast<uint64_t>(st * kTileStep);
         const uint32_t a = tmem_P + (j % 3) * 64;
+        if (!(kAblate && (p.ablate & 4))) {
 #pragma unroll
-        for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)
-          umma_bf16_ts_elect(tmem_O, a + kk * 8, dv + 128 * kk, idesc_o, (j > 0) || (kk != 0));
+          for (int kk = 0; kk < kAttnBlockKV / 16; ++kk)
+            umma_bf16_ts_elect(tmem_O, a + kk * 8, dv + 128 * kk, idesc_o, (j > 0) || (kk != 0));
+        }
         umma_commit_elect(&v_empty[st]);
         umma_commit_elect(&p_free[j % 3]);
         umma_commit_elect(&pv_done[j & 1]);
@@ -685,8 +693,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       // warp's S -> reference latency is on the per-block critical chain s_free -> S -> max -> m_ready)
       float mx = -INFINITY;
       uint32_t v[64];
+      if (kAblate && (p.ablate & 8)) mx = 0.f;
 #pragma unroll
       for (int c = 0; c < 128; c += 64) {
+        if (kAblate && (p.ablate & 8)) break;
         if (kParts == 4) {  // 736 threads leave 80 registers: a single 64-register load does not fit next to its context
           tmem_ld_32x32b_x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(v));
           tmem_ld_32x32b_x32(t_s + c + 32, *reinterpret_cast<uint32_t(*)[32]>(v + 32));
@@ -892,8 +902,13 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             if (!a3_is_poly_pair(q, kPoly)) {
-              e[2 * q] = ex2_approx_ordered(t[2 * q]);
-              e[2 * q + 1] = ex2_approx_ordered(t[2 * q + 1]);
+              if (kAblate && (p.ablate & 1)) {
+                e[2 * q] = t[2 * q];
+                e[2 * q + 1] = t[2 * q + 1];
+              } else {
+                e[2 * q] = ex2_approx_ordered(t[2 * q]);
+                e[2 * q + 1] = ex2_approx_ordered(t[2 * q + 1]);
+              }
             }
           if (c == 0) {
             // the second chunk has landed by now: all of my S(j) is in registers, and the sooner the MMA warp may
@@ -905,8 +920,13 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 #pragma unroll
           for (int q = 8; q < 16; ++q)
             if (!a3_is_poly_pair(q, kPoly)) {
-              e[2 * q] = ex2_approx_ordered(t[2 * q]);
-              e[2 * q + 1] = ex2_approx_ordered(t[2 * q + 1]);
+              if (kAblate && (p.ablate & 1)) {
+                e[2 * q] = t[2 * q];
+                e[2 * q + 1] = t[2 * q + 1];
+              } else {
+                e[2 * q] = ex2_approx_ordered(t[2 * q]);
+                e[2 * q + 1] = ex2_approx_ordered(t[2 * q + 1]);
+              }
             }
           // the polynomial pairs: plain (non-volatile) FMA-pipe code, free to be scheduled between the MUFUs above
 #pragma unroll
@@ -917,15 +937,21 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         ready16(e, 16);
         if (tr) AT_TRACE(c == 0 ? 50 : 55);
         uint32_t pk[16];
+        if (kAblate && (p.ablate & 16)) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          add2_acc(rs0, rs1, e[i + 0], e[i + 1]);
-          add2_acc(rs2, rs3, e[i + 2], e[i + 3]);
-          pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
-          pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
+          for (int i = 0; i < 16; ++i) pk[i] = __float_as_uint(e[2 * i]) ^ __float_as_uint(e[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            add2_acc(rs0, rs1, e[i + 0], e[i + 1]);
+            add2_acc(rs2, rs3, e[i + 2], e[i + 3]);
+            pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
+            pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
+          }
         }
         if (tr && c == 0) AT_TRACE(51);
-        tmem_st_32x32b_x16(t_p + (c >> 1), pk);
+        if (!(kAblate && (p.ablate & 2))) tmem_st_32x32b_x16(t_p + (c >> 1), pk);
+        else asm volatile("" ::"r"(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]));
         if (tr && c == 0) AT_TRACE(57);
         if (tr) AT_TRACE(c == 0 ? 54 : 56);
       }
@@ -1072,6 +1098,8 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
@@ -1088,6 +1116,7 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   p.Tk = Tk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
+  p.ablate = 0;
   const dim3 grid((Tq + kAttnBlockQ - 1) / kAttnBlockQ, B * H);
   const bool trace = p.trace != nullptr;  // the phase stamps are compiled out of the production instantiations
   if (g_attn_parts == 0) {
@@ -1109,6 +1138,14 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
       case -1: fn = attn_fwd_pipelined_kernel<true>; break;
       case 2: fn = attn_fwd_pipelined_kernel<false, 2, 2>; break;
       default: break;
+    }
+    static const int ablate = [] {
+      const char* e = getenv("ST_ATTN_ABLATE");
+      return e ? atoi(e) : 0;
+    }();
+    if (ablate && !trace) {
+      p.ablate = ablate;
+      fn = attn_fwd_pipelined_kernel<false, 2, 0, true>;
     }
     launch_kernel(fn, dim3(grid), dim3(kA3Threads), kA3SmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");

@@ -721,8 +721,9 @@ int main(int argc, char** argv) {
                    argc > 8 ? atoi(argv[8]) : 1, atoi(argv[6]), true);
     return g_fail ? 1 : 0;
   }
-  if (!strcmp(what, "conv1") && argc >= 8) {  // selftest conv1 N H W C K block_n
-    test_conv_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), true, false,
+  if (!strcmp(what, "conv1") && argc >= 8) {  // selftest conv1 N H W C K block_n [mode: 0 temb (default), 1 residual, 2 plain]
+    const int mode = argc >= 9 ? atoi(argv[8]) : 0;
+    test_conv_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), mode == 0, mode == 1,
                    atoi(argv[7]), true);
     return g_fail ? 1 : 0;
   }

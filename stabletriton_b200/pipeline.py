@@ -15,8 +15,10 @@ repo's oracle restatement (oracle/unet_oracle.py: euler_sigmas / denoise_loop).
 
 Multi-GPU: one process per GPU, full weight replica, prompts sharded across ranks,
 no collective inside the loop; one all-gather of the final latents at the end.  Special case
-`cfg_split` (2 ranks, one prompt): rank 0 runs the uncond row, rank 1 the cond row, and a per-step
-all-gather of eps (131 KB at 1024^2) joins them inside the step.
+`cfg_split` (2 ranks, one prompt): rank 0 runs the uncond row, rank 1 the cond row, and the two eps rows
+(131 KB each at 1024^2) meet inside the step -- either through an NCCL all-gather captured in the step graph
+(`exchange="nccl"`) or through ONE kernel that stores the row into the peer GPU's memory over NVLink and applies
+the Euler update as soon as the peer's row has landed (`exchange="peer"`, csrc/peer.cu).
 """
 from __future__ import annotations
 
@@ -52,6 +54,77 @@ def euler_schedule(num_inference_steps: int, num_train_timesteps: int = 1000, be
     return (torch.tensor(timesteps, dtype=torch.float32), torch.tensor(sigmas, dtype=torch.float32), init_noise_sigma)
 
 
+class PeerExchange:
+    """The pair of NVLink-mapped exchange slabs behind `st_cfg_exchange_euler_update` (csrc/peer.cu): this rank's slab
+    (cudaMalloc, exported as a CUDA IPC handle) and the peer's, mapped into this process.  torch.distributed only carries
+    the two 64-byte handles, once; the per-step data never touches NCCL or the host."""
+
+    def __init__(self, n_elems: int, device, group=None):
+        import ctypes
+
+        import torch.distributed as dist
+
+        assert dist.is_initialized() and dist.get_world_size(group) == 2, "the CFG split runs on exactly two ranks"
+        self.device = torch.device(device)
+        self.rank = dist.get_rank(group)
+        self.group = group
+        L = _cabi._load()
+        with torch.cuda.device(self.device):
+            # Every rank walks through the same collectives whatever fails locally (a rank that raised early would leave
+            # its peer waiting in the next collective); the outcome is agreed on at the end.
+            self.local = self.peer = None
+            failure = None
+            handle = ctypes.create_string_buffer(64)
+            try:
+                nbytes = int(L.st_peer_slab_bytes(n_elems))
+                ptr = ctypes.c_void_p()
+                _cabi.check(L.st_peer_alloc(nbytes, ctypes.byref(ptr)), "peer_alloc")
+                self.local = ptr.value
+                _cabi.check(L.st_peer_export(self.local, handle), "peer_export")
+            except Exception as exc:  # noqa: BLE001
+                failure = exc
+            handles = [None, None]
+            dist.all_gather_object(handles, None if failure else handle.raw, group=group)
+            if failure is None and handles[1 - self.rank] is not None:
+                try:
+                    peer = ctypes.c_void_p()
+                    _cabi.check(L.st_peer_import(handles[1 - self.rank], ctypes.byref(peer)), "peer_import")
+                    self.peer = peer.value
+                except Exception as exc:  # noqa: BLE001
+                    failure = exc
+            ok = torch.tensor([1 if (failure is None and self.peer is not None) else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also: both slabs are mapped before anybody stores
+            if int(ok.item()) == 0:
+                self.close()
+                raise _cabi.StableTritonError(
+                    f"peer-memory exchange is not available between the two ranks ({failure!r}); "
+                    f"use DenoiseLoop(..., exchange='nccl')")
+        self.n = n_elems
+
+    def error(self) -> int:
+        """Sequence number of an exchange that timed out waiting for the peer (0: none).  Host read: not inside capture."""
+        import ctypes
+        out = ctypes.c_uint(0)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            _cabi.check(_cabi._load().st_peer_error(self.local, ctypes.byref(out)), "peer_error")
+        return int(out.value)
+
+    def close(self) -> None:
+        """Collective (both ranks): unmap the peer's slab, then free the local one."""
+        L = _cabi._load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            if self.peer is not None:
+                _cabi.check(L.st_peer_close(self.peer), "peer_close")
+            import torch.distributed as dist
+            if dist.is_initialized():  # the exporter must not free a slab the importer still has mapped
+                dist.barrier(self.group)
+            if self.local is not None:
+                _cabi.check(L.st_peer_free(self.local), "peer_free")
+        self.local = self.peer = None
+
+
 class DenoiseLoop:
     """Euler + CFG loop for `prompts` prompts at a fixed latent size, one graph replay per step.
 
@@ -61,7 +134,7 @@ class DenoiseLoop:
 
     def __init__(self, unet, prompts: int, latent_hw: int, num_steps: int = 30, guidance: float = 5.0,
                  in_channels: int = 4, device="cuda", cfg_row: Optional[int] = None, group=None,
-                 hoist_prompt_constants: bool = True):
+                 hoist_prompt_constants: bool = True, exchange: str = "nccl"):
         self.unet_fn = getattr(unet, "eager_forward", unet)
         # compile() also exposes the graph split at the prompt / step boundary: K/V projections of the text context and
         # the text / time-ids embedding are computed in set_conditioning(), not in every step
@@ -87,8 +160,16 @@ class DenoiseLoop:
         self.added: Dict[str, torch.Tensor] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._eps_pair = None
-        if cfg_row is not None:
+        # CFG split: how the two eps rows meet every step -- "nccl": all_gather_into_tensor + the Euler kernel (two graph
+        # nodes through NCCL); "peer": one kernel that stores the row into the peer GPU's memory over NVLink, waits for
+        # the peer's row and applies the Euler update (csrc/peer.cu)
+        assert exchange in ("nccl", "peer"), exchange
+        self.exchange = exchange if cfg_row is not None else None
+        self.peer: Optional[PeerExchange] = None
+        if cfg_row is not None and exchange == "nccl":
             self._eps_pair = torch.empty((2,) + tuple(self.model_in.shape), dtype=torch.bfloat16, device=dev)
+        elif cfg_row is not None:
+            self.peer = PeerExchange(self.x.numel(), dev, group)
 
     # -- one step, as launched into the current stream ---------------------------------------------
     def _step_body(self):
@@ -104,6 +185,13 @@ class DenoiseLoop:
             eps = self.unet_fn(self.model_in, self.t_cur, self.ctx, self.added)[0]
         if not eps.is_contiguous():
             eps = eps.contiguous()
+        if self.peer is not None:
+            _cabi.check(L.st_cfg_exchange_euler_update(eps.data_ptr(), int(self.cfg_row), self.peer.local, self.peer.peer,
+                                                       self.x.data_ptr(), n, self.guidance, self.sigmas.data_ptr(),
+                                                       self.step.data_ptr(), stream), "cfg_exchange_euler_update")
+            _cabi.check(L.st_advance_step(self.step.data_ptr(), self.t_cur.data_ptr(), self.timesteps.data_ptr(), stream),
+                        "advance_step")
+            return eps
         if self.cfg_row is None:
             eps_u, eps_c = eps[: self.P], eps[self.P:]
         else:

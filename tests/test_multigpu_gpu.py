@@ -6,7 +6,9 @@
   * CFG split: one prompt on two GPUs, rank 0 = uncond row, rank 1 = cond row, a per-step NCCL all-gather of eps CAPTURED
     INSIDE the step graph (`DenoiseLoop(cfg_row=...)`) -- final latents identical on both ranks and bit-equal to the
     single-GPU loop that evaluates the two rows one after the other (the engine is not batch-invariant bit for bit:
-    GroupNorm splits its pixel range by the number of images), and within 1e-3 of the ordinary batch-2 loop.
+    GroupNorm splits its pixel range by the number of images), and within 1e-3 of the ordinary batch-2 loop;
+  * the same split with `exchange="peer"`: each rank stores its eps row into the other GPU's memory over NVLink and
+    applies the Euler update in the same kernel (csrc/peer.cu) -- bit-equal to the NCCL path, no time-out flagged.
 
 Skipped unless two CUDA devices are visible (run with `gpurun --gpus 2`).
 """
@@ -40,7 +42,27 @@ def _slice(d, lo, hi):
     return {k: v[lo:hi] for k, v in d.items()}
 
 
+WORKER_LIMIT_S = 240  # a rank still running after this dumps every thread's stack and exits (never a silent hang)
+
+
 def _worker(rank, world, port, out_dir):
+    import faulthandler
+    import sys
+    import traceback
+
+    faulthandler.dump_traceback_later(WORKER_LIMIT_S, exit=True, file=sys.stderr)
+    try:
+        _worker_body(rank, world, port, out_dir)
+    except BaseException:  # noqa: BLE001 -- print NOW: the peer may be parked in a collective and never let us unwind
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+    faulthandler.cancel_dump_traceback_later()
+
+
+def _worker_body(rank, world, port, out_dir):
+    import sys
+
     import torch.distributed as dist
 
     import stabletriton_b200 as st
@@ -52,29 +74,43 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     device = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
-    try:
-        cfg = UNetConfig.tiny()
-        compiled = st.compile(synth.build_unet(cfg, seed=3, device=device), cuda_graph=True)
-        noise = synth.synth_tensor("latents", (PROMPTS, cfg.in_channels, LATENT, LATENT), 77, device=device) * (3.0 ** 0.5)
-        cond, uncond = _conditioning(cfg, PROMPTS, 1, device), _conditioning(cfg, PROMPTS, 2, device)
+    cfg = UNetConfig.tiny()
+    compiled = st.compile(synth.build_unet(cfg, seed=3, device=device), cuda_graph=True)
+    noise = synth.synth_tensor("latents", (PROMPTS, cfg.in_channels, LATENT, LATENT), 77, device=device) * (3.0 ** 0.5)
+    cond, uncond = _conditioning(cfg, PROMPTS, 1, device), _conditioning(cfg, PROMPTS, 2, device)
 
-        # ---- prompt sharding + final all-gather --------------------------------------------------------------
-        lo, hi = shard_prompts(PROMPTS, world, rank)
-        loop = DenoiseLoop(compiled, prompts=hi - lo, latent_hw=LATENT, num_steps=STEPS, device=device)
-        local = loop.run(noise[lo:hi], _slice(cond, lo, hi), _slice(uncond, lo, hi), use_graph=True)
-        full = gather_latents(local, PROMPTS)
-        assert full.shape == (PROMPTS, cfg.in_channels, LATENT, LATENT) and full.is_cuda
-        assert torch.equal(full[lo:hi], local)
+    # ---- prompt sharding + final all-gather --------------------------------------------------------------
+    lo, hi = shard_prompts(PROMPTS, world, rank)
+    loop = DenoiseLoop(compiled, prompts=hi - lo, latent_hw=LATENT, num_steps=STEPS, device=device)
+    local = loop.run(noise[lo:hi], _slice(cond, lo, hi), _slice(uncond, lo, hi), use_graph=True)
+    full = gather_latents(local, PROMPTS)
+    assert full.shape == (PROMPTS, cfg.in_channels, LATENT, LATENT) and full.is_cuda
+    assert torch.equal(full[lo:hi], local)
 
-        # ---- CFG split: per-step all-gather of eps inside the captured step graph -----------------------------
-        split = DenoiseLoop(compiled, prompts=1, latent_hw=LATENT, num_steps=STEPS, device=device, cfg_row=rank)
-        x_split = split.run(noise[:1], _slice(cond, 0, 1), _slice(uncond, 0, 1), use_graph=True)
-        assert split.graph is not None
-        x_again = split.run(noise[:1], _slice(cond, 0, 1), _slice(uncond, 0, 1), use_graph=True)  # replay of the same graph
-        assert torch.equal(x_split, x_again)
-        torch.save({"full": full.cpu(), "split": x_split.cpu()}, os.path.join(out_dir, f"rank{rank}.pt"))
-    finally:
-        dist.destroy_process_group()
+    # ---- CFG split: per-step all-gather of eps inside the captured step graph -----------------------------
+    split = DenoiseLoop(compiled, prompts=1, latent_hw=LATENT, num_steps=STEPS, device=device, cfg_row=rank)
+    x_split = split.run(noise[:1], _slice(cond, 0, 1), _slice(uncond, 0, 1), use_graph=True)
+    assert split.graph is not None
+    x_again = split.run(noise[:1], _slice(cond, 0, 1), _slice(uncond, 0, 1), use_graph=True)  # replay of the same graph
+    assert torch.equal(x_split, x_again)
+    # ---- same split, eps exchanged by peer stores over NVLink inside ONE kernel with the Euler update -------
+    fused = DenoiseLoop(compiled, prompts=1, latent_hw=LATENT, num_steps=STEPS, device=device, cfg_row=rank,
+                        exchange="peer")
+    x_peer = fused.run(noise[:1], _slice(cond, 0, 1), _slice(uncond, 0, 1), use_graph=True)
+    x_peer2 = fused.run(noise[:1], _slice(cond, 0, 1), _slice(uncond, 0, 1), use_graph=True)
+    assert fused.peer.error() == 0, "an exchange timed out waiting for the peer"
+    assert torch.equal(x_peer, x_peer2)
+    assert torch.equal(x_peer, x_split), "peer-memory exchange must reproduce the NCCL all-gather path bit for bit"
+    fused.peer.close()
+    torch.save({"full": full.cpu(), "split": x_split.cpu(), "peer": x_peer.cpu()}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    torch.cuda.synchronize(device)
+    # No destroy_process_group(): with captured NCCL collectives still alive in this process (the step graphs above) the
+    # communicator teardown was observed to park both ranks forever (first 2-GPU run of this test, 15 minutes).  The
+    # results are on disk; leave without unwinding.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 class _RowByRow:
@@ -97,10 +133,20 @@ def test_two_rank_nccl_sharding_and_cfg_split(built_lib, tmp_path):
     from stabletriton_b200.pipeline import DenoiseLoop, shard_prompts
 
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ctx = mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=False)
+    import time
+    deadline = time.time() + WORKER_LIMIT_S + 60
+    try:
+        while not ctx.join(timeout=5):  # raises ProcessRaisedException / ProcessExitedException if a rank failed
+            assert time.time() < deadline, "the NCCL ranks did not finish in time"
+    finally:
+        for proc in ctx.processes:
+            if proc.is_alive():
+                proc.kill()
     got = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
     assert torch.equal(got[0]["full"], got[1]["full"]), "all-gather must give every rank the same latents"
     assert torch.equal(got[0]["split"], got[1]["split"]), "both CFG-split ranks must hold the same latents"
+    assert torch.equal(got[0]["peer"], got[1]["peer"]) and torch.equal(got[0]["peer"], got[0]["split"])
 
     # single-GPU references, computed in this process
     device = torch.device("cuda", 0)
