@@ -27,6 +27,16 @@
 
 namespace st {
 
+// One mbarrier arrival per WARP: every lane has finished (and fenced) its own tensor-memory / shared-memory accesses,
+// __syncwarp orders them before lane 0's releasing arrive.  Per-thread arrivals looked harmless but are serialised
+// read-modify-writes on one shared-memory word -- 640 of them per K/V block in the pipelined kernel (s_free, p_full,
+// m_ready), which turned out to BE its ~1.45 k-cycle block period: switching whole stages of the pipeline off left
+// the time unchanged (profiles/r02_attention_experiments.txt, section 3).
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 constexpr int kAttnBlockQ = 128;
 constexpr int kAttnBlockKV = 128;
 constexpr int kAttnD = 64;
@@ -91,9 +101,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
+    mbar_init(p_full, 8);   // one arrival per softmax warp (warp_arrive)
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 256);
+    mbar_init(o_empty, 8);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<kAttnTmemCols>(tmem_slot);
@@ -223,7 +233,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_32x32b_x32(tmem_O + lane_off + half * 32, o);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(o_empty);
+        warp_arrive(o_empty, lane);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = (acc[i] + __uint_as_float(o[i])) * alpha;
       }
@@ -263,7 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(6);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      warp_arrive(p_full, lane);
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(7);
     }
     {
@@ -348,7 +358,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     mbar_init(qk_full, 1);
     mbar_init(v_full, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 4);  // one arrival per softmax warp
     mbar_init(o_full, 1);
     mbar_fence_init();
   }
@@ -452,7 +462,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(p_full);
+    warp_arrive(p_full, lane);
     const float inv = 1.f / ((l0 + l1) + (l2 + l3));
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -536,7 +546,7 @@ __host__ __device__ constexpr bool a3_is_poly_pair(int q, int poly) { return ((q
 
 // kAblate: timing-only instantiation for bottleneck hunting -- p.ablate bits switch pieces of the pipeline off (1: no MUFU
 // in the exp warps, 2: no tcgen05.st of P, 4: P.V MMAs not issued, 8: max warps do not read S, 16: no row sums / bf16
-// packs, 32: S MMAs not issued).  Results are wrong by construction; never selected unless ST_ATTN_ABLATE is set.
+// packs, 32: S MMAs not issued, 64: no K/V TMA loads after the first ring pass, 128: exp warps do not read S).  Results are wrong by construction; never selected unless ST_ATTN_ABLATE is set.
 template <bool kTrace, int kParts = 2, int kPoly = 0, bool kAblate = false>
 __global__ void __launch_bounds__(A3Layout<kParts>::kThreads, 1)
 attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -584,12 +594,12 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&m_ready[i], 128);
+      mbar_init(&m_ready[i], 4);  // one arrival per warp (warp_arrive)
       mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 128 * kParts);
+      mbar_init(&s_free[i], 4 * kParts);
     }
     for (int i = 0; i < 3; ++i) {
-      mbar_init(&p_full[i], 128 * kParts);
+      mbar_init(&p_full[i], 4 * kParts);
       mbar_init(&p_free[i], 1);
     }
     mbar_fence_init();
@@ -616,10 +626,19 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kA3Stages;
         const uint32_t ph = (j / kA3Stages) & 1;
+        if (kAblate && (p.ablate & 64) && j >= kA3Stages) {  // no K/V traffic after the first ring pass
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive(&k_full[st]);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive(&v_full[st]);
+          continue;
+        }
         mbar_wait(&k_empty[st], ph ^ 1);
+        if (j == 20) AT_TRACE(44);
         mbar_expect_tx(&k_full[st], kAttnTileBytes);
         tma_load_4d(sK + st * kAttnTileBytes, &tmap_k, &k_full[st], 0, j * kAttnBlockKV, h, b);
         mbar_wait(&v_empty[st], ph ^ 1);
+        if (j == 20) AT_TRACE(45);
         mbar_expect_tx(&v_full[st], kAttnTileBytes);
         tma_load_4d(sV + st * kAttnTileBytes, &tmap_v, &v_full[st], 0, j * kAttnBlockKV, h, b);
       }
@@ -657,7 +676,9 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       for (int j = 0; j + 2 < nkv; ++j) {
         mbar_wait(&s_free[j & 1], (j >> 1) & 1);
         tc_fence_after();
+        if (j == 16 && lane == 0) AT_TRACE(58);
         issue_s(j + 2);
+        if (j == 16 && lane == 0) AT_TRACE(59);
       }
     } else {
       const uint64_t desc_v0 = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
@@ -665,8 +686,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         const int st = j % kA3Stages;
         mbar_wait(&p_full[j % 3], (j / 3) & 1);
         if (j == 2 && lane == 0) AT_TRACE(8);
+        if (j == 16 && lane == 0) AT_TRACE(60);
         mbar_wait(&v_full[st], (j / kA3Stages) & 1);
         tc_fence_after();
+        if (j == 16 && lane == 0) AT_TRACE(61);
         const uint64_t dv = desc_v0 + static_cast<uint64_t>(st * kTileStep);
         const uint32_t a = tmem_P + (j % 3) * 64;
         if (!(kAblate && (p.ablate & 4))) {
@@ -678,6 +701,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         umma_commit_elect(&p_free[j % 3]);
         umma_commit_elect(&pv_done[j & 1]);
         if (j == 2 && lane == 0) AT_TRACE(9);
+        if (j == 16 && lane == 0) AT_TRACE(62);
       }
     }
   } else if (warp >= L::kMaxWarp0) {  // four warps, one per TMEM lane quadrant
@@ -688,6 +712,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       const int valid = p.Tk - j * kAttnBlockKV;  // columns >= valid are padding
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
+      if (j == 18 && warp == L::kMaxWarp0 && lane == 0) AT_TRACE(46);
       const uint32_t t_s = tmem_S + buf * 128 + lane_off;
       // two 64-column loads, one TMEM round trip each (four 32-column loads took ~900 cycles per block, and this
       // warp's S -> reference latency is on the per-block critical chain s_free -> S -> max -> m_ready)
@@ -745,11 +770,12 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       // (its own barrier per buffer: the next arrival on p_free[j % 3] is P(j).V(j), which needs this very m(j), so
       // the parity wait cannot alias)
       if (j >= 3) mbar_wait(&p_free[j % 3], (j / 3 - 1) & 1);
+      if (j == 18 && warp == L::kMaxWarp0 && lane == 0) AT_TRACE(47);
       tc_fence_before();
       if (j == 2 && warp == L::kMaxWarp0 && lane == 0) AT_TRACE(12);
       if (kParts == 2 && (j == 16 || j == 17) && lane == 0) AT_TRACE(16 * (j - 15) + 8 + warp - L::kMaxWarp0);
       if (j == 3 && warp == L::kMaxWarp0 && lane == 0) AT_TRACE(13);
-      mbar_arrive(&m_ready[buf]);  // release: the exp warps' wait acquires s_m and orders the O rescale before P(j)
+      warp_arrive(&m_ready[buf], lane);  // release: the exp warps' wait acquires s_m and orders the O rescale before P(j)
     }
   } else if (kParts == 4) {
     // ===================================== exp warps, 4 per quadrant ========================
@@ -773,25 +799,31 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       }
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&s_free[buf]);  // my share of S(j) is in registers: S(j+2) may overwrite the buffer
+      warp_arrive(&s_free[buf], lane);  // my share of S(j) is in registers: S(j+2) may overwrite the buffer
       if (valid < 32) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (i >= valid) cur[i] = 0xff800000u;  // -inf -> 2^(-inf) = 0
       }
       float e[32];
+      {
+        // t = s * c - m as packed pairs (FFMA2), then the 32 exponentials back to back
+        float t[32];
+        const float neg_m = -m;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) e[i] = ex2_approx_ordered(fmaf(__uint_as_float(cur[i]), p.scale_log2, -m));
+        for (int q = 0; q < 16; ++q)
+          fma2_bcast(__uint_as_float(cur[2 * q]), __uint_as_float(cur[2 * q + 1]), p.scale_log2, neg_m, t[2 * q], t[2 * q + 1]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = ex2_approx_ordered(t[i]);
+      }
       ready16(e, 0);
       ready16(e, 16);
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        rs0 += e[i + 0];
-        rs1 += e[i + 1];
-        rs2 += e[i + 2];
-        rs3 += e[i + 3];
+        add2_acc(rs0, rs1, e[i + 0], e[i + 1]);
+        add2_acc(rs2, rs3, e[i + 2], e[i + 3]);
         pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
         pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
       }
@@ -799,7 +831,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       tmem_st_32x32b_x16(tmem_P + (j % 3) * 64 + lane_off + part * 16, pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[j % 3]);
+      warp_arrive(&p_full[j % 3], lane);
     }
     {
       mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
@@ -850,10 +882,14 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         // the max warps arrive on m_ready(j) after they have seen s_full(j): S(j) is complete
         mbar_wait(&m_ready[buf], (j >> 1) & 1);
         tc_fence_after();
-        tmem_ld_32x32b_x32(t_s, va);
+        if (!(kAblate && (p.ablate & 128))) tmem_ld_32x32b_x32(t_s, va);
         m = s_m[buf * 128 + row];
       } else {
         m = m_pre;
+      }
+      if (kTrace && j == 17 && warp == 2 && lane == 0) {
+        AT_TRACE(31);
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[15] = pre ? 1 : 2;
       }
       if (j == 2 && warp == 2 && lane == 0) AT_TRACE(2);
       if (m != m_prev) {
@@ -870,14 +906,14 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       for (int c = 0; c < 64; c += 32) {
         uint32_t(&cur)[32] = ((c >> 5) & 1) ? vb : va;
         if (c == 0) {
-          tmem_ld_32x32b_x32(t_s + 32, vb);
+          if (!(kAblate && (p.ablate & 128))) tmem_ld_32x32b_x32(t_s + 32, vb);
         } else {
           pre = false;
           if (j + 1 < nkv) {
             const bool ok = mbar_test_wait(&m_ready[buf ^ 1], ((j + 1) >> 1) & 1);  // a poll, never a suspend
             if (__all_sync(0xffffffffu, ok)) {  // tcgen05.ld is warp-collective: decide as a warp
               tc_fence_after();
-              tmem_ld_32x32b_x32(tmem_S + (buf ^ 1) * 128 + lane_off + half * 64, va);
+              if (!(kAblate && (p.ablate & 128))) tmem_ld_32x32b_x32(tmem_S + (buf ^ 1) * 128 + lane_off + half * 64, va);
               m_pre = s_m[(buf ^ 1) * 128 + row];
               pre = true;
             }
@@ -915,7 +951,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
             // overwrite this S buffer with S(j+2), the sooner the max warps get to publish m(j+2)
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&s_free[buf]);
+            warp_arrive(&s_free[buf], lane);
           }
 #pragma unroll
           for (int q = 8; q < 16; ++q)
@@ -961,8 +997,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       // touch TMEM.  (Publishing later -- after that phase -- was measured: the tcgen05.st of the next chunk then
       // queues behind the running MMA for ~250 cycles.)
       tmem_st_wait();
+      if (tr) AT_TRACE(28);
       tc_fence_before();
-      mbar_arrive(&p_full[j % 3]);
+      if (tr) AT_TRACE(29);
+      warp_arrive(&p_full[j % 3], lane);
       if (tr) AT_TRACE(52);
     }
     float acc[32];
@@ -1037,7 +1075,7 @@ static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int 
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static unsigned long long* g_attn_trace = nullptr;
-constexpr int kAttnDefaultParts = 2;
+constexpr int kAttnDefaultParts = 4;  // 16 exp warps: -0.16 ms on the attention launches of a step (gpu_call19)
 static int g_attn_parts = 0;  // 0: not decided yet (ST_ATTN_PARTS or the default)
 constexpr int kAttnDefaultPoly = 0;
 static int g_attn_poly = -1;  // -1: not decided yet (ST_ATTN_POLY or the default)
@@ -1100,6 +1138,8 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<true, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
@@ -1123,29 +1163,30 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
     const char* e = getenv("ST_ATTN_PARTS");  // exp warps per TMEM lane quadrant: 2 or 4
     g_attn_parts = (e && e[0] == '4') ? 4 : ((e && e[0] == '2') ? 2 : kAttnDefaultParts);
   }
-  const int parts = g_attn_parts;
-  if (pipelined && parts == 4 && !trace) {
+  if (g_attn_poly < 0) {
+    const char* e = getenv("ST_ATTN_POLY");  // polynomial pairs out of every 8: 0 or 2 (a quarter of the exponentials)
+    g_attn_poly = (e && e[0] == '2') ? 2 : ((e && e[0] == '0') ? 0 : kAttnDefaultPoly);
+  }
+  static const int ablate = [] {
+    const char* e = getenv("ST_ATTN_ABLATE");
+    return e ? atoi(e) : 0;
+  }();
+  // the phase stamps, the polynomial share and the ablation switches exist in the 8-exp-warp layout only
+  const int parts = (trace || g_attn_poly == 2 || ablate) ? 2 : g_attn_parts;
+  if (pipelined && parts == 4) {
     launch_kernel(attn_fwd_pipelined_kernel<false, 4>, dim3(grid), dim3(A3Layout<4>::kThreads), kA3SmemBytes,
                   static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
   } else if (pipelined) {
-    if (g_attn_poly < 0) {
-      const char* e = getenv("ST_ATTN_POLY");  // polynomial pairs out of every 8: 0 or 2 (a quarter of the exponentials)
-      g_attn_poly = (e && e[0] == '2') ? 2 : ((e && e[0] == '0') ? 0 : kAttnDefaultPoly);
-    }
     auto fn = attn_fwd_pipelined_kernel<false, 2, 0>;
     switch (trace ? -1 : g_attn_poly) {
       case -1: fn = attn_fwd_pipelined_kernel<true>; break;
       case 2: fn = attn_fwd_pipelined_kernel<false, 2, 2>; break;
       default: break;
     }
-    static const int ablate = [] {
-      const char* e = getenv("ST_ATTN_ABLATE");
-      return e ? atoi(e) : 0;
-    }();
-    if (ablate && !trace) {
+    if (ablate) {
       p.ablate = ablate;
-      fn = attn_fwd_pipelined_kernel<false, 2, 0, true>;
+      fn = trace ? attn_fwd_pipelined_kernel<true, 2, 0, true> : attn_fwd_pipelined_kernel<false, 2, 0, true>;
     }
     launch_kernel(fn, dim3(grid), dim3(kA3Threads), kA3SmemBytes, static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");

@@ -752,6 +752,20 @@ int main(int argc, char** argv) {
                            "chunk 0: sums + packs done", "chunk 0: tcgen05.st issued", "chunk 1 in registers",
                            "chunk 1: 32 ex2 done", "chunk 1 stored", "P(16) published"};
       for (int i = 0; i < 9; ++i) printf("    warp 2  %-40s %8lld\n", dn[i], (long long)(h[order[i]] - h[48]));
+      if (h[28])
+        printf("    warp 2  tail: tcgen05.wait::st done %lld, fence done %lld, arrived %lld; block 17: loop top %lld, reference known %lld (prefetched: %s)\n",
+               (long long)(h[28] - h[48]), (long long)(h[29] - h[48]), (long long)(h[52] - h[48]), (long long)(h[32] - h[48]),
+               (long long)(h[31] - h[48]), h[15] == 1 ? "yes" : "no");
+      printf("    warp 2  block 16 loop top -> reference known: %lld cycles\n", (long long)(h[48] - h[16]));
+    }
+    {
+      const int extra[9] = {58, 59, 60, 61, 62, 46, 47, 44, 45};
+      const char* en[9] = {"S issuer: s_free(16) seen", "S issuer: S(18) issued + committed", "PV issuer: p_full(16) seen",
+                           "PV issuer: v_full(16) seen", "PV issuer: P(16).V(16) issued + committed",
+                           "max warp: s_full(18) seen", "max warp: p_free for m(18) seen", "TMA: k_empty for K(20) seen",
+                           "TMA: v_empty for V(20) seen"};
+      for (int i = 0; i < 9; ++i)
+        if (h[extra[i]]) printf("  %-42s %8lld\n", en[i], (long long)(h[extra[i]] - h[0]));
     }
     test_attn_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), true, true);
     return g_fail ? 1 : 0;

@@ -501,6 +501,7 @@ def test_attention_polynomial_exp2_share(K):
     q, k, v = rnd(b, tq, h * 64, seed=50) * 2.0, rnd(b, tk, h * 64, seed=51) * 2.0, rnd(b, tk, h * 64, seed=52)
     ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
     try:
+        L.st_debug_set_attention_parts(2)  # the polynomial share exists in the 8-exp-warp layout
         L.st_debug_set_attention_poly(0)
         base = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
         L.st_debug_set_attention_poly(2)
@@ -508,6 +509,7 @@ def test_attention_polynomial_exp2_share(K):
         torch.cuda.synchronize()
     finally:
         L.st_debug_set_attention_poly(-1)
+        L.st_debug_set_attention_parts(0)
     check(poly.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
     rel, cos = parity(poly.float(), base.float())
     assert rel <= 8e-3 and cos >= 0.99999, (rel, cos)

@@ -64,6 +64,39 @@ __global__ void bench(float* out, long long* cyc, int iters) {
         for (int i = 0; i < 8; ++i) h[i] = ex2_f16x2(h[i]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc ^= h[i];
+    } else if (MODE == 6) {  // the attention chunk: 8 FFMA2 + 16 EX2 + 8 FADD2 + 8 F2FP (packed pairs)
+      float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; i += 2)
+        asm volatile("{.reg .b64 a, b, c, d; mov.b64 a, {%0, %1}; mov.b64 b, {%2, %2}; mov.b64 c, {%3, %3};\n"
+                     "fma.rn.ftz.f32x2 d, a, b, c; mov.b64 {%0, %1}, d;}" : "+f"(x[i]), "+f"(x[i + 1]) : "f"(0.99f), "f"(-0.01f));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = ex2(x[i]);
+#pragma unroll
+      for (int i = 0; i < 16; i += 2)
+        asm volatile("{.reg .b64 a, b; mov.b64 a, {%0, %1}; mov.b64 b, {%2, %3}; add.rn.ftz.f32x2 a, a, b; mov.b64 {%0, %1}, a;}"
+                     : "+f"(f0), "+f"(f1) : "f"(x[i]), "f"(x[i + 1]));
+      facc += f0 + f1;
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) acc ^= pack(x[i], x[i + 1]);
+    } else if (MODE == 7) {  // 16 EX2 + 8 integer-op packs (round-to-nearest-even by hand + PRMT): no F2FP
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = ex2(x[i]);
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        uint32_t a = __float_as_uint(x[i]), b = __float_as_uint(x[i + 1]);
+        a += 0x7fffu + ((a >> 16) & 1u);
+        b += 0x7fffu + ((b >> 16) & 1u);
+        acc ^= __byte_perm(a, b, 0x7632);
+      }
+    } else if (MODE == 8) {  // 16 EX2 + 16 independent FFMA (does FMA-pipe work issue under the MUFU stream?)
+      float y[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y[i] = fmaf(x[i], 0.99f, -0.01f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = ex2(x[i]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) facc += y[i];
     } else if (MODE == 4) {  // 8 packs done with integer ops instead (round-to-nearest-even by hand: 4 ALU ops / pair)
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
@@ -106,5 +139,8 @@ int main() {
   run<3>("16 x (FFMA, EX2, FADD) + 8 x F2FP", 56);
   run<4>("8 x bf16 pack by integer ops", 8);
   run<5>("8 x F2FP.F16 + 32 x EX2.F16x2 (64 exps)", 40);
+  run<6>("8 FFMA2 + 16 EX2 + 8 FADD2 + 8 F2FP (attention chunk)", 40);
+  run<7>("16 EX2 + 8 integer-op bf16 packs", 24);
+  run<8>("16 EX2 + 16 FFMA + 16 FADD", 48);
   return 0;
 }
