@@ -64,7 +64,13 @@ def time_graph(fns, iters=10):
 
 
 def bench_case(name, make, bytes_per_set, work, unit, peak):
-    """make() -> a callable bound to a FRESH set of buffers.  work = algorithmic bytes or FLOPs per launch."""
+    """make() -> a callable bound to a FRESH set of buffers.  work = algorithmic bytes or FLOPs per launch.
+    Every case starts from an idle GPU (1 s pause): the first version of this table timed the convolutions right after
+    the 0.8 ms 8192^3 GEMM replays and reported them at 0.42 of peak -- power-capped clocks, not the kernel
+    (tools/conv_probe.py: the same launches run at 1000-1050 TFLOP/s from idle)."""
+    import time
+    torch.cuda.synchronize()
+    time.sleep(1.0)
     rot = max(2, min(64, int(2.5 * L2_BYTES / max(bytes_per_set, 1)) + 1))
     cold = time_graph([make() for _ in range(rot)])
     one = make()
@@ -132,6 +138,14 @@ def main():
             return lambda: K.conv2d(x, w, bias, residual=r, w_static=True)
         nbytes = (n * c * hw * hw + kk * c * 9 + 2 * n * kk * hw * hw) * 2
         add(bench_case(f"conv3x3 N={n} C={c} {hw}x{hw} K={kk} +bias+residual", make, nbytes,
+                       2.0 * n * hw * hw * kk * c * 9, "TFLOP/s", tf_sus))
+
+        def make_temb(n=n, c=c, hw=hw, kk=kk):  # resnet conv1: + bias + time-embedding row, GroupNorm partials emitted
+            x = nhwc(n, c, hw, hw)
+            w = K.pack_conv_weight(rand(kk, c, 3, 3, scale=(9 * c) ** -0.5))
+            bias, temb = rand(kk), rand(n, kk)
+            return lambda: K.conv2d(x, w, bias, temb=temb, w_static=True, gn_stats=True)
+        add(bench_case(f"conv3x3 N={n} C={c} {hw}x{hw} K={kk} +bias+temb+gn-partials", make_temb, nbytes,
                        2.0 * n * hw * hw * kk * c * 9, "TFLOP/s", tf_sus))
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
