@@ -24,6 +24,14 @@ static int cluster_policy() {
   return v;
 }
 
+static int drain_all_policy() {
+  static const int v = [] {
+    const char* e = getenv("ST_GEMM_DRAIN");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v;
+}
+
 static bool pair_possible(int M, int block_n, bool geglu) {
   const int mb = (M + kGemmBlockM - 1) / kGemmBlockM;
   if (mb % 2 != 0) return false;  // vertically adjacent tiles pair up
@@ -260,6 +268,7 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.ws = sk_ws;
   p.flags = sk_flags;
   p.cluster = pair ? 1 : 0;
+  p.drain_all = drain_all_policy();
   p.gn_part = static_cast<float*>(gn_partial);
 
   CUtensorMap ta, tb;
@@ -350,6 +359,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.ws = sk_ws;
   p.flags = sk_flags;
   p.cluster = pair ? 1 : 0;
+  p.drain_all = drain_all_policy();
   p.gn_part = static_cast<float*>(gn_partial);
   p.conv_H = H;
   p.conv_W = W;

@@ -54,6 +54,7 @@ struct GemmParams {
   int stream_k;
   int w_static;  // W is not written by the preceding kernel: prefetch it ahead of the PDL wait
   int cluster;   // host-side choice: launch the CTA-pair instantiation
+  int drain_all; // debug (ST_GEMM_DRAIN=1): wait for the bulk stores' global writes before exit, not just their smem reads
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
   // GroupNorm statistics of the OUTPUT, emitted by the epilogue (the consumer GroupNorm then needs no statistics pass
@@ -658,7 +659,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         acc_phase ^= 1;
       }
     }
-    if (etid == 0) tma_store_wait_all();  // smem must outlive the last bulk store
+    // Shared memory must outlive the last bulk store's READ of the staging tile; the global writes themselves are ordinary
+    // in-flight stores that grid completion (and the dependent kernel's griddepcontrol.wait) covers -- waiting for them
+    // here kept every CTA ~1.5 k cycles longer on the exit path of the single-wave launches (p.drain_all: A/B switch).
+    if (etid == 0) {
+      if (p.drain_all)
+        tma_store_wait_all();
+      else
+        tma_store_wait_read();
+    }
   }
 
   tc_fence_before();
