@@ -53,6 +53,7 @@ struct AttnParams {
   float scale_log2;
   unsigned long long* trace;  // debug: 16 clock64 stamps for CTA (0,0), or nullptr
   int ablate;                 // debug (ST_ATTN_ABLATE, timing only -- results are wrong): see attn_fwd_pipelined_kernel<.., kAblate>
+  unsigned wait_hint_ns, wait_sleep_ns;  // TMA / issuer / max warps of the pipelined kernel: mbar_wait_relaxed parameters
 };
 
 // Registers are allocated per group of 4 warps: the 10 warps of this CTA cost as much as 12, so two resident
@@ -580,6 +581,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   const int h = blockIdx.y - b * p.H;
   const int nkv = (p.Tk + kAttnBlockKV - 1) / kAttnBlockKV;
   if (threadIdx.x == 0) AT_TRACE(0);
+#define A3_WAIT(bar, parity) mbar_wait_relaxed(bar, parity, p.wait_hint_ns, p.wait_sleep_ns)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -627,17 +629,17 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         const int st = j % kA3Stages;
         const uint32_t ph = (j / kA3Stages) & 1;
         if (kAblate && (p.ablate & 64) && j >= kA3Stages) {  // no K/V traffic after the first ring pass
-          mbar_wait(&k_empty[st], ph ^ 1);
+          A3_WAIT(&k_empty[st], ph ^ 1);
           mbar_arrive(&k_full[st]);
-          mbar_wait(&v_empty[st], ph ^ 1);
+          A3_WAIT(&v_empty[st], ph ^ 1);
           mbar_arrive(&v_full[st]);
           continue;
         }
-        mbar_wait(&k_empty[st], ph ^ 1);
+        A3_WAIT(&k_empty[st], ph ^ 1);
         if (j == 20) AT_TRACE(44);
         mbar_expect_tx(&k_full[st], kAttnTileBytes);
         tma_load_4d(sK + st * kAttnTileBytes, &tmap_k, &k_full[st], 0, j * kAttnBlockKV, h, b);
-        mbar_wait(&v_empty[st], ph ^ 1);
+        A3_WAIT(&v_empty[st], ph ^ 1);
         if (j == 20) AT_TRACE(45);
         mbar_expect_tx(&v_full[st], kAttnTileBytes);
         tma_load_4d(sV + st * kAttnTileBytes, &tmap_v, &v_full[st], 0, j * kAttnBlockKV, h, b);
@@ -656,7 +658,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       const uint64_t desc_k0 = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
       auto issue_s = [&](int j) {
         const int st = j % kA3Stages;
-        mbar_wait(&k_full[st], (j / kA3Stages) & 1);
+        A3_WAIT(&k_full[st], (j / kA3Stages) & 1);
         tc_fence_after();
         const uint64_t dk = desc_k0 + static_cast<uint64_t>(st * kTileStep);
         const uint32_t d = tmem_S + (j & 1) * 128;
@@ -667,14 +669,14 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         umma_commit_elect(&k_empty[st]);
         umma_commit_elect(&s_full[j & 1]);
       };
-      mbar_wait(q_full, 0);
+      A3_WAIT(q_full, 0);
       issue_s(0);
       if (nkv > 1) issue_s(1);
       // S(j+2) goes out as soon as the exp warps have pulled S(j) out of TMEM (s_free, a quarter into block j); the
       // max warps read S(j) before that (the exp warps wait for m_ready(j)).  So the S -> max -> reference chain of
       // block j+2 starts well over a block ahead of its use.
       for (int j = 0; j + 2 < nkv; ++j) {
-        mbar_wait(&s_free[j & 1], (j >> 1) & 1);
+        A3_WAIT(&s_free[j & 1], (j >> 1) & 1);
         tc_fence_after();
         if (j == 16 && lane == 0) AT_TRACE(58);
         issue_s(j + 2);
@@ -684,10 +686,10 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       const uint64_t desc_v0 = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kA3Stages;
-        mbar_wait(&p_full[j % 3], (j / 3) & 1);
+        A3_WAIT(&p_full[j % 3], (j / 3) & 1);
         if (j == 2 && lane == 0) AT_TRACE(8);
         if (j == 16 && lane == 0) AT_TRACE(60);
-        mbar_wait(&v_full[st], (j / kA3Stages) & 1);
+        A3_WAIT(&v_full[st], (j / kA3Stages) & 1);
         tc_fence_after();
         if (j == 16 && lane == 0) AT_TRACE(61);
         const uint64_t dv = desc_v0 + static_cast<uint64_t>(st * kTileStep);
@@ -710,7 +712,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     for (int j = 0; j < nkv; ++j) {
       const int buf = j & 1;
       const int valid = p.Tk - j * kAttnBlockKV;  // columns >= valid are padding
-      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      A3_WAIT(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
       if (j == 18 && warp == L::kMaxWarp0 && lane == 0) AT_TRACE(46);
       const uint32_t t_s = tmem_S + buf * 128 + lane_off;
@@ -749,7 +751,7 @@ attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       const float m_new = move ? mj : m;
       if (j > 0 && __any_sync(0xffffffffu, move)) {
         const float f = ex2_approx(m - m_new);  // exactly 1 for rows that keep their reference
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // every P.V issued so far has landed in O
+        A3_WAIT(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // every P.V issued so far has landed in O
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 64; c += 32) {
@@ -1078,6 +1080,7 @@ static unsigned long long* g_attn_trace = nullptr;
 constexpr int kAttnDefaultParts = 4;  // 16 exp warps: -0.16 ms on the attention launches of a step (gpu_call19)
 static int g_attn_parts = 0;  // 0: not decided yet (ST_ATTN_PARTS or the default)
 constexpr int kAttnDefaultPoly = 0;
+constexpr unsigned kAttnDefaultWaitHint = 1000, kAttnDefaultWaitSleep = 0;  // hint: T = 4096 622 -> 632 TFLOP/s (gpu_call25)
 static int g_attn_poly = -1;  // -1: not decided yet (ST_ATTN_POLY or the default)
 
 }  // namespace st
@@ -1157,6 +1160,10 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
   p.ablate = 0;
+  static const unsigned wait_hint = [] { const char* e = getenv("ST_ATTN_WAIT_HINT"); return e ? (unsigned)atoi(e) : kAttnDefaultWaitHint; }();
+  static const unsigned wait_sleep = [] { const char* e = getenv("ST_ATTN_WAIT_SLEEP"); return e ? (unsigned)atoi(e) : kAttnDefaultWaitSleep; }();
+  p.wait_hint_ns = wait_hint;
+  p.wait_sleep_ns = wait_sleep;
   const dim3 grid((Tq + kAttnBlockQ - 1) / kAttnBlockQ, B * H);
   const bool trace = p.trace != nullptr;  // the phase stamps are compiled out of the production instantiations
   if (g_attn_parts == 0) {

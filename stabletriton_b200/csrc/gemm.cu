@@ -24,10 +24,19 @@ static int cluster_policy() {
   return v;
 }
 
+constexpr int kGemmDefaultSpin = 0;
 static int drain_all_policy() {
   static const int v = [] {
     const char* e = getenv("ST_GEMM_DRAIN");
     return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v;
+}
+
+static int spin_wait_policy() {
+  static const int v = [] {
+    const char* e = getenv("ST_GEMM_SPIN");
+    return e ? atoi(e) & 3 : kGemmDefaultSpin;
   }();
   return v;
 }
@@ -269,6 +278,7 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.flags = sk_flags;
   p.cluster = pair ? 1 : 0;
   p.drain_all = drain_all_policy();
+  p.spin_wait = spin_wait_policy();
   p.gn_part = static_cast<float*>(gn_partial);
 
   CUtensorMap ta, tb;
@@ -360,6 +370,7 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   p.flags = sk_flags;
   p.cluster = pair ? 1 : 0;
   p.drain_all = drain_all_policy();
+  p.spin_wait = spin_wait_policy();
   p.gn_part = static_cast<float*>(gn_partial);
   p.conv_H = H;
   p.conv_W = W;

@@ -54,6 +54,9 @@ struct GemmParams {
   int stream_k;
   int w_static;  // W is not written by the preceding kernel: prefetch it ahead of the PDL wait
   int cluster;   // host-side choice: launch the CTA-pair instantiation
+  int spin_wait; // bit 0: the MMA warp polls full_bar (mbarrier.test_wait) instead of try_wait, bit 1: the producer polls
+                 // empty_bar -- a suspended waiter is woken ~300 cycles late, and in a ring that is latency-bound
+                 // (CTA pairs: 7 stages against a ~2850-cycle round trip) both waits block on every k-block
   int drain_all; // debug (ST_GEMM_DRAIN=1): wait for the bulk stores' global writes before exit, not just their smem reads
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
@@ -287,7 +290,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (b_in_flight) {
             --prefetched;
           } else {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (p.spin_wait & 2)
+              mbar_wait_spin(&empty_bar[stage], phase ^ 1);
+            else
+              mbar_wait(&empty_bar[stage], phase ^ 1);
             arm(&full_bar[stage]);
           }
           if (kConvA) {
@@ -331,7 +337,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (p.spin_wait & 1)
+            mbar_wait_spin(&full_bar[stage], phase);
+          else
+            mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (first_seg && kb == kb0 && lane == 0) ST_TRACE(2);
           const uint64_t da = desc_a0 + static_cast<uint64_t>(stage * kStageStep);

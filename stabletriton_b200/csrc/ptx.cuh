@@ -76,6 +76,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Waiters with slack: `hint_ns` > 0 passes a suspend-time hint to try_wait (the thread may stay parked that long before
+// the instruction answers "not yet"), `sleep_ns` > 0 sleeps between attempts.  Both cut the number of SYNCS instructions
+// a waiting warp pushes through the MIO queue, which it shares with MUFU / LDS / tcgen05.ld of the working warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns, uint32_t sleep_ns) {
+  while (true) {
+    uint32_t ok;
+    if (hint_ns) {
+      asm volatile(
+          "{\n\t.reg .pred P;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, P;\n\t}\n"
+          : "=r"(ok)
+          : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+          : "memory");
+    } else {
+      ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+    }
+    if (ok) return;
+    if (sleep_ns) __nanosleep(sleep_ns);
+  }
+}
+
 // Busy poll.  mbar_wait (try_wait) lets the hardware suspend the thread, and a suspended waiter is woken ~300 cycles
 // after the phase completes (measured in the attention pipeline, where three such hand-offs sat on the per-block
 // critical path).  For waits that are latency critical and whose warp has nothing else to do.

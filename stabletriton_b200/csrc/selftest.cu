@@ -716,6 +716,44 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
+  if (!strcmp(what, "ctrace") && argc >= 8) {  // selftest ctrace N H W C K block_n : per-CTA phase timeline of a 3x3 conv
+    const int N = atoi(argv[2]), H = atoi(argv[3]), W = atoi(argv[4]), C = atoi(argv[5]), K = atoi(argv[6]);
+    const int bn = atoi(argv[7]);
+    __nv_bfloat16* x = dev_bf16((size_t)N * H * W * C, 1.0f);
+    __nv_bfloat16* w = dev_bf16((size_t)K * 9 * C, 0.03f);
+    __nv_bfloat16* b = dev_bf16(K, 0.5f);
+    __nv_bfloat16* t = dev_bf16((size_t)N * K, 1.0f);
+    __nv_bfloat16* y;
+    CK(cudaMalloc(&y, (size_t)N * H * W * K * 2));
+    unsigned long long* tr;
+    CK(cudaMalloc(&tr, 148 * 12 * 8));
+    for (int it = 0; it < 3; ++it) ST(st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, nullptr, ST_W_STATIC, bn, nullptr, 0));
+    CK(cudaMemset(tr, 0, 148 * 12 * 8));
+    st_debug_set_gemm_trace(tr);
+    ST(st_conv3x3_nhwc_bf16(x, w, b, y, N, H, W, C, K, t, K, nullptr, ST_W_STATIC, bn, nullptr, 0));
+    CK(cudaDeviceSynchronize());
+    st_debug_set_gemm_trace(nullptr);
+    std::vector<unsigned long long> h(148 * 12);
+    CK(cudaMemcpy(h.data(), tr, 148 * 12 * 8, cudaMemcpyDeviceToHost));
+    const char* names[6] = {"setup", "first operands landed", "MMA issue done (tile 0)", "accumulator ready",
+                            "epilogue tile 0 done", "exit"};
+    printf("conv3x3 N=%d %dx%d C=%d K=%d bn=%d: %d k-blocks per tile\n", N, H, W, C, K, bn, 9 * C / 64);
+    for (int e = 1; e <= 6; ++e) {
+      double sum = 0, mn = 1e18, mx = 0;
+      int cnt = 0;
+      for (int c = 0; c < 148; ++c) {
+        if (!h[c * 12] || !h[c * 12 + e]) continue;
+        const double d = (double)(h[c * 12 + e] - h[c * 12]);
+        sum += d;
+        mn = d < mn ? d : mn;
+        mx = d > mx ? d : mx;
+        ++cnt;
+      }
+      printf("  t[%d] %-26s cycles since CTA start: min %8.0f avg %8.0f max %8.0f (n=%d)\n", e, names[e - 1], mn,
+             cnt ? sum / cnt : 0, mx, cnt);
+    }
+    return 0;
+  }
   if (!strcmp(what, "gemm1") && argc >= 7) {  // selftest gemm1 M N K flags block_n [bias res]: one timed case (ncu target)
     test_gemm_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), (unsigned)atoi(argv[5]), argc > 7 ? atoi(argv[7]) : 1,
                    argc > 8 ? atoi(argv[8]) : 1, atoi(argv[6]), true);
