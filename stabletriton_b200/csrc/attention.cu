@@ -502,14 +502,14 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
 // ------------------------------------------------------------------------------------------------
 // Pipelined variant for Tk > 128 (self-attention): ONE CTA per SM that owns all 512 TMEM columns, so S and P
-// are double-buffered and O accumulates in TMEM across the whole K/V sweep; 480 threads, warp-specialised:
+// are double-buffered and O accumulates in TMEM across the whole K/V sweep; warp-specialised (warp numbers for the
+// 8-exp-warp layout, kParts = 2; with kParts = 4 the exp warps are 2-17 and the rest follow):
 //
 //   warp 0      TMA producer: Q once, K and V rings (4 stages each)
 //   warp 14     S issuer:     S(0), S(1); for j: wait s_free(j) -> S(j+2)          (S runs two blocks ahead)
 //   warp 1      P.V issuer:   for j: wait P(j) -> O += P(j) V(j)
-//   warps 2-9   exp warps:    two per TMEM lane quadrant, each owning half of every row: stream S(j) out of TMEM
-//               in 16-column chunks (next chunk in flight while this one is processed), p = 2^(s*c - m),
-//               packed bf16 P(j) -> TMEM, partial row sums.  Nothing but the MUFU-bound stream.
+//   warps 2-9   exp warps:    kParts per TMEM lane quadrant, each owning a column slice of every row: stream S(j) out of
+//               TMEM in 32-column chunks, p = 2^(s*c - m), packed bf16 P(j) -> TMEM, partial row sums.
 //   warps 10-13 max warps:    one thread per row, run one block AHEAD of the exp warps: exact row max of S(j)
 //               (FMNMX3), decide the row's reference m, publish it through shared memory.  m only moves when
 //               the row max grows by more than 2^8 (lazy rescale: P <= 256, fp32 sums are safe); moving it
@@ -522,10 +522,11 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 // the two-CTA kernel above spends ~2.7 k cycles per block and SM because each CTA's MMA -> max -> exp -> MMA
 // chain is serial (single S / P buffers in 256 columns) and both CTAs hit the MUFU phase together.
 constexpr int kA3Stages = 4;
-// kParts exp warps per TMEM lane quadrant, each owning 128 / kParts score columns of every row.  2: the round-1 layout
-// (480 threads, two 32-column chunks per warp and block, next block's first chunk prefetched).  4: 16 exp warps (736
-// threads, <= 88 registers), one 32-column chunk per warp and block -- four instruction streams per scheduler instead
-// of two to cover the TMEM / barrier latencies that leave the MUFU pipe half idle (ncu: pipe_xu 49 %).
+// kParts exp warps per TMEM lane quadrant, each owning 128 / kParts score columns of every row.  4 (the default): 16 exp
+// warps (736 threads, 78 registers), one 32-column chunk per warp and block -- four instruction streams per scheduler to
+// cover the TMEM / barrier latencies of each warp's serial chain (ncu: pipe_xu 64 % busy against 49 % with two).  2: the
+// round-1 layout (480 threads, two 32-column chunks per warp and block, next block's first chunk prefetched); the trace,
+// polynomial and ablation instantiations exist in this layout only.
 template <int kParts>
 struct A3Layout {
   static constexpr int kExpWarps = 4 * kParts;
@@ -547,7 +548,8 @@ __host__ __device__ constexpr bool a3_is_poly_pair(int q, int poly) { return ((q
 
 // kAblate: timing-only instantiation for bottleneck hunting -- p.ablate bits switch pieces of the pipeline off (1: no MUFU
 // in the exp warps, 2: no tcgen05.st of P, 4: P.V MMAs not issued, 8: max warps do not read S, 16: no row sums / bf16
-// packs, 32: S MMAs not issued, 64: no K/V TMA loads after the first ring pass, 128: exp warps do not read S).  Results are wrong by construction; never selected unless ST_ATTN_ABLATE is set.
+// packs, 32: S MMAs not issued, 64: no K/V TMA loads after the first ring pass, 128: exp warps do not read S).  Results
+// are wrong by construction; never selected unless ST_ATTN_ABLATE is set.
 template <bool kTrace, int kParts = 2, int kPoly = 0, bool kAblate = false>
 __global__ void __launch_bounds__(A3Layout<kParts>::kThreads, 1)
 attn_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,

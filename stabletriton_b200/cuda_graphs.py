@@ -117,7 +117,10 @@ class GraphedCallable:
                     fn(*self.static_args, **self.static_kwargs)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, pool=env.mempool, stream=env.stream):
+            # thread_local: another host thread driving ANOTHER device (its own env, its own capture or plain cudaMalloc)
+            # must not invalidate this capture -- the default "global" mode does (first 2-GPU run of
+            # test_two_devices_from_two_threads_of_one_process: "operation failed due to a previous error during capture")
+            with torch.cuda.graph(self.graph, pool=env.mempool, stream=env.stream, capture_error_mode="thread_local"):
                 self.static_outputs = fn(*self.static_args, **self.static_kwargs)
             torch.cuda.synchronize()
 

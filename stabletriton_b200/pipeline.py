@@ -250,7 +250,7 @@ class DenoiseLoop:
             torch.cuda.synchronize(self.device)
             self.step.zero_()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
                 self._last_eps = self._step_body()
         torch.cuda.synchronize(self.device)
         self.x.copy_(saved[0])
