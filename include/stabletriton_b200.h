@@ -37,6 +37,9 @@ extern "C" {
                            the stream, so its first tiles may be fetched before the programmatic (PDL) dependency on
                            that kernel resolves.  Results are identical with or without it.                       */
 
+#define ST_EPI_F32OUT 8u /* st_gemm_bf16 only: D is fp32 [M, ldd] (ldd in fp32 elements, N % 4 == 0); not with GEGLU /
+                            GroupNorm partials.  For results that feed a row softmax (the 512-wide VAE attention head). */
+
 typedef void* st_stream_t; /* a cudaStream_t / CUstream */
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -183,6 +186,19 @@ int st_scale_model_input(const float* x, void* model_in, long long n, int copies
 int st_euler_cfg_update(const void* eps_uncond, const void* eps_cond, float* x, long long n, float guidance,
                         const float* sigmas, const int* step, st_stream_t stream);
 int st_advance_step(int* step, float* t_out, const float* timesteps, st_stream_t stream);
+
+/* 1x1 convolution between tiny channel counts (Ci, Co <= 8), dense NCHW in and out, input pre-scaled by in_scale:
+ * y[n, o, :] = b[o] + sum_i w[o, i] * in_scale * x[n, i, :].  The VAE's post_quant_conv on the latent (Diffusers
+ * AutoencoderKL.decode: z / scaling_factor -> post_quant_conv); w is [Co, Ci] bf16. */
+int st_pointwise_conv_small_bf16(const void* x, const void* w, const void* bias, void* y, int N, long long HW, int Ci,
+                                 int Co, float in_scale, st_stream_t stream);
+
+/* ---- row softmax (VAE mid-block attention) -------------------------------
+ * P[i, :] = softmax(scale * S[i, :]) for fp32 scores S [M, lds] (from st_gemm_bf16 with ST_EPI_F32OUT) into bf16
+ * probabilities P [M, ldp]; N % 4 == 0.  The SDXL VAE decoder's attention has ONE head of width 512 over H*W tokens
+ * (Diffusers AutoencoderKL mid block): Q K^T and P V run on st_gemm_bf16, this kernel sits between them. */
+int st_softmax_rows_f32_bf16(const float* S, long long lds, void* P, long long ldp, int M, int N, float scale,
+                             st_stream_t stream);
 
 /* ---- 2-GPU CFG split: eps exchange over NVLink peer memory, fused with the Euler update -----------
  * (one prompt on two GPUs, rank 0 = uncond row, rank 1 = cond row; the reference has no

@@ -45,6 +45,8 @@ PROTOTYPES = {
     "st_scale_model_input": (I, [P, P, LL, I, P, P, P]),
     "st_euler_cfg_update": (I, [P, P, P, LL, F, P, P, P]),
     "st_advance_step": (I, [P, P, P, P]),
+    "st_softmax_rows_f32_bf16": (I, [P, LL, P, LL, I, I, F, P]),
+    "st_pointwise_conv_small_bf16": (I, [P, P, P, P, I, LL, I, I, F, P]),
     "st_peer_slab_bytes": (c_size_t, [LL]),
     "st_peer_alloc": (I, [c_size_t, ctypes.POINTER(c_void_p)]),
     "st_peer_free": (I, [P]),
@@ -58,6 +60,7 @@ PROTOTYPES = {
 ST_EPI_SILU = 1
 ST_EPI_GEGLU = 2
 ST_W_STATIC = 4
+ST_EPI_F32OUT = 8
 
 
 class StableTritonError(RuntimeError):

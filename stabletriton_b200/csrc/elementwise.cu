@@ -413,6 +413,31 @@ __global__ void advance_step_kernel(int* step, float* t_out, const float* timest
   if (t_out && timesteps) *t_out = timesteps[s];
 }
 
+// ---- 1x1 convolution between tiny channel counts (<= 8 -> <= 8), NCHW in, NCHW out ----------------
+// The VAE's post_quant_conv (4 -> 4 on the latent, Diffusers AutoencoderKL.decode): 16 multiply-adds per pixel, far too
+// small for the tensor-core GEMM (K would be padded from 4 to 64).  y[n, o, p] = b[o] + sum_i w[o, i] * in_scale * x[n, i, p].
+__global__ void pointwise_conv_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                            const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, int N,
+                                            long long HW, int Ci, int Co, float in_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  float wr[64], br[8];
+  for (int i = 0; i < Co * Ci; ++i) wr[i] = __bfloat162float(w[i]) * in_scale;
+  for (int o = 0; o < Co; ++o) br[o] = b ? __bfloat162float(b[o]) : 0.f;
+  const long long total = static_cast<long long>(N) * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+    float xi[8];
+    for (int c = 0; c < Ci; ++c) xi[c] = __bfloat162float(x[(n * Ci + c) * HW + p]);
+    for (int o = 0; o < Co; ++o) {
+      float acc = br[o];
+      for (int c = 0; c < Ci; ++c) acc = fmaf(wr[o * Ci + c], xi[c], acc);
+      y[(n * Co + o) * HW + p] = __float2bfloat16(acc);
+    }
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int grid_for(long long total, int block, int max_blocks_per_sm = 8) {
   long long g = (total + block - 1) / block;
@@ -567,6 +592,18 @@ int st_nhwc_to_nchw_bf16(const void* src, int ld, void* dst, int N, int HW, int 
   launch_kernel(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
                 static_cast<const __nv_bfloat16*>(src), ld, static_cast<__nv_bfloat16*>(dst), N, HW, C);
   ST_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+  return ST_OK;
+}
+
+int st_pointwise_conv_small_bf16(const void* x, const void* w, const void* bias, void* y, int N, long long HW, int Ci,
+                                 int Co, float in_scale, st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(x && w && y, "pointwise_conv_small: null pointer");
+  ST_CHECK_ARG(N > 0 && HW > 0 && Ci > 0 && Ci <= 8 && Co > 0 && Co <= 8, "pointwise_conv_small: channel counts must be in [1, 8]");
+  launch_kernel(pointwise_conv_small_kernel, dim3(grid_for(static_cast<long long>(N) * HW, 256)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
+                static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), N, HW, Ci, Co, in_scale);
+  ST_CHECK_LAUNCH("pointwise_conv_small_kernel");
   return ST_OK;
 }
 

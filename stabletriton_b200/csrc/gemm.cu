@@ -222,6 +222,8 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   ST_CHECK_ARG(lda >= K && ldw >= K, "gemm: lda/ldw smaller than K");
   ST_CHECK_ARG(aligned16(A) && aligned16(W) && aligned16(D), "gemm: pointers must be 16-byte aligned");
   const bool geglu = (flags & ST_EPI_GEGLU) != 0;
+  const bool out_f32 = (flags & ST_EPI_F32OUT) != 0;
+  ST_CHECK_ARG(!out_f32 || (!geglu && !gn_partial), "gemm: the fp32 output mode excludes GEGLU and GroupNorm partials");
   ST_CHECK_ARG(!geglu || N % 2 == 0, "gemm: GEGLU needs an even N");
   const int n_out = geglu ? N / 2 : N;
   ST_CHECK_ARG(n_out % 8 == 0, "gemm: output width (%d) must be a multiple of 8", n_out);
@@ -241,7 +243,7 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
     block_n = tc.block_n;
     pair = tc.pair;
     const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
-    if (!geglu && !gn_partial && !pair && want_stream_k(mb * ((n_out + 255) / 256), K / kGemmBlockK, mb * ((n_out + block_n - 1) / block_n),
+    if (!geglu && !gn_partial && !out_f32 && !pair && want_stream_k(mb * ((n_out + 255) / 256), K / kGemmBlockK, mb * ((n_out + block_n - 1) / block_n),
                                 &sk_ws, &sk_flags)) {
       stream_k = true;
       block_n = 256;
@@ -280,6 +282,8 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   p.drain_all = drain_all_policy();
   p.spin_wait = spin_wait_policy();
   p.gn_part = static_cast<float*>(gn_partial);
+  p.out_f32 = out_f32 ? 1 : 0;
+  const int ldd_map = out_f32 ? 2 * ldd : ldd;  // the (unused) store maps describe the fp32 rows as twice as many bf16
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, M, K, lda, kGemmBlockM);
@@ -287,9 +291,9 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   rc = make_tmap_2d(&tb, W, N, K, ldw, (geglu || p.cluster) ? block_n / 2 : block_n);  // one box per B load
   if (rc != ST_OK) return rc;
   CUtensorMap td, tdt;
-  rc = make_tmap_2d(&td, D, M, n_out, ldd, kGemmBlockM);
+  rc = make_tmap_2d(&td, D, M, n_out, ldd_map, kGemmBlockM);
   if (rc != ST_OK) return rc;
-  rc = make_tmap_2d(&tdt, D, M, n_out, ldd, kGemmBlockM, 32, /*swizzle128=*/false);  // 32-column tail group of a 160-wide tile
+  rc = make_tmap_2d(&tdt, D, M, n_out, ldd_map, kGemmBlockM, 32, /*swizzle128=*/false);  // 32-column tail group of a 160-wide tile
   if (rc != ST_OK) return rc;
   return dispatch_gemm<false>(ta, tb, td, tdt, p, block_n, geglu, static_cast<cudaStream_t>(stream));
 }

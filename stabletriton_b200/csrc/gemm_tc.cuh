@@ -54,6 +54,9 @@ struct GemmParams {
   int stream_k;
   int w_static;  // W is not written by the preceding kernel: prefetch it ahead of the PDL wait
   int cluster;   // host-side choice: launch the CTA-pair instantiation
+  int out_f32;   // D is fp32 [M, ldd] (ST_EPI_F32OUT): written with plain 16-byte stores, one 128-byte line per thread and
+                 // 32-column chunk -- for results whose bf16 rounding would be amplified downstream (attention scores
+                 // of the 512-wide VAE head ahead of a row softmax)
   int spin_wait; // bit 0: the MMA warp polls full_bar (mbarrier.test_wait) instead of try_wait, bit 1: the producer polls
                  // empty_bar -- a suspended waiter is woken ~300 cycles late, and in a ring that is latency-bound
                  // (CTA pairs: 7 stages against a ~2850-cycle round trip) both waits block on every k-block
@@ -582,6 +585,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 x[j + 2 * e + 1] += f.y;
               }
             }
+        }
+        if (p.out_f32) {  // uniform over the CTA: nobody stages, nobody waits on the staging barriers below
+          if (row_ok && !dead) {
+            float* drow = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (n0 + c + j < p.n_out) *reinterpret_cast<float4*>(drow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+          }
+          continue;
         }
         // staging tile: [128 rows][64 cols] bf16, 128-byte swizzle (16-byte chunk ^= row & 7)
 #pragma unroll

@@ -493,6 +493,98 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ------------------------------------------------------------------------------------------------
+// Row softmax of fp32 scores into bf16 probabilities: P[i, :] = softmax(scale * S[i, :]).  One CTA per row; rows of up to
+// 16 384 columns are held in registers (one read, one write), longer ones are streamed twice (online max / sum, then the
+// write pass; the second read is served by L2).  Used by the single-head, 512-wide attention of the VAE mid block, whose
+// scores come out of st_gemm_bf16(..., ST_EPI_F32OUT): no flash kernel covers head_dim 512, and a bf16 score matrix would
+// put 2^-8 relative rounding under an exponential.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmThreads = 256;
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < kSmThreads / 32; ++w) r = fmaxf(r, red[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < kSmThreads / 32; ++w) r += red[w];  // fixed order: bit-reproducible
+  __syncthreads();
+  return r;
+}
+
+template <int kVec>  // float4 vectors per thread held in registers; 0: streaming
+__global__ void __launch_bounds__(kSmThreads)
+softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P, long long ldp, int N,
+                    float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[kSmThreads / 32];
+  const float4* srow = reinterpret_cast<const float4*>(S + static_cast<size_t>(blockIdx.x) * lds);
+  uint2* prow = reinterpret_cast<uint2*>(P + static_cast<size_t>(blockIdx.x) * ldp);
+  const int nvec = N >> 2;
+  if (kVec > 0) {
+    float4 v[kVec > 0 ? kVec : 1];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      const int i = threadIdx.x + k * kSmThreads;
+      v[k] = i < nvec ? __ldcs(srow + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      mx = fmaxf(fmaxf(mx, fmaxf(v[k].x, v[k].y)), fmaxf(v[k].z, v[k].w));
+    }
+    mx = block_max(mx, red);
+    const float off = mx * scale_log2;  // scale > 0: max commutes with it
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      v[k].x = ex2_approx(fmaf(v[k].x, scale_log2, -off));
+      v[k].y = ex2_approx(fmaf(v[k].y, scale_log2, -off));
+      v[k].z = ex2_approx(fmaf(v[k].z, scale_log2, -off));
+      v[k].w = ex2_approx(fmaf(v[k].w, scale_log2, -off));
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float inv = 1.f / block_sum(sum, red);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) {
+      const int i = threadIdx.x + k * kSmThreads;
+      if (i < nvec) prow[i] = make_uint2(pack_bf16x2(v[k].x * inv, v[k].y * inv), pack_bf16x2(v[k].z * inv, v[k].w * inv));
+    }
+  } else {
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < nvec; i += kSmThreads) {
+      const float4 q = srow[i];
+      mx = fmaxf(fmaxf(mx, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+    }
+    mx = block_max(mx, red);
+    const float off = mx * scale_log2;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < nvec; i += kSmThreads) {
+      const float4 q = srow[i];
+      sum += (ex2_approx(fmaf(q.x, scale_log2, -off)) + ex2_approx(fmaf(q.y, scale_log2, -off))) +
+             (ex2_approx(fmaf(q.z, scale_log2, -off)) + ex2_approx(fmaf(q.w, scale_log2, -off)));
+    }
+    const float inv = 1.f / block_sum(sum, red);
+    for (int i = threadIdx.x; i < nvec; i += kSmThreads) {
+      const float4 q = srow[i];
+      prow[i] = make_uint2(pack_bf16x2(ex2_approx(fmaf(q.x, scale_log2, -off)) * inv, ex2_approx(fmaf(q.y, scale_log2, -off)) * inv),
+                           pack_bf16x2(ex2_approx(fmaf(q.z, scale_log2, -off)) * inv, ex2_approx(fmaf(q.w, scale_log2, -off)) * inv));
+    }
+  }
+}
+
 }  // namespace st
 
 extern "C" {
@@ -640,6 +732,28 @@ int st_layernorm_bf16(const void* x, int ldx, void* y, int ldy, const void* gamm
   }
 #undef ST_LN_CASE
   ST_CHECK_LAUNCH("layernorm_kernel");
+  return ST_OK;
+}
+
+int st_softmax_rows_f32_bf16(const float* S, long long lds, void* P, long long ldp, int M, int N, float scale,
+                             st_stream_t stream) {
+  using namespace st;
+  ST_CHECK_ARG(S && P, "softmax_rows: null pointer");
+  ST_CHECK_ARG(M > 0 && N > 0 && N % 4 == 0, "softmax_rows: N (%d) must be a positive multiple of 4", N);
+  ST_CHECK_ARG(scale > 0.f, "softmax_rows: scale must be positive");
+  ST_CHECK_ARG(lds >= N && lds % 4 == 0 && ldp >= N && ldp % 4 == 0, "softmax_rows: bad row pitch");
+  ST_CHECK_ARG(aligned16(S) && (reinterpret_cast<uintptr_t>(P) & 7) == 0, "softmax_rows: S must be 16-byte, P 8-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* pp = static_cast<__nv_bfloat16*>(P);
+  const float sl2 = scale * 1.4426950408889634f;
+  const int nvec = N / 4;
+  if (nvec <= 4 * kSmThreads)
+    launch_kernel(softmax_rows_kernel<4>, dim3(M), dim3(kSmThreads), 0, s, S, lds, pp, ldp, N, sl2);
+  else if (nvec <= 16 * kSmThreads)
+    launch_kernel(softmax_rows_kernel<16>, dim3(M), dim3(kSmThreads), 0, s, S, lds, pp, ldp, N, sl2);
+  else
+    launch_kernel(softmax_rows_kernel<0>, dim3(M), dim3(kSmThreads), 0, s, S, lds, pp, ldp, N, sl2);
+  ST_CHECK_LAUNCH("softmax_rows_kernel");
   return ST_OK;
 }
 

@@ -24,7 +24,7 @@ from typing import Optional
 import torch
 
 from . import _cabi
-from ._cabi import ST_EPI_GEGLU, ST_EPI_SILU, ST_W_STATIC, check, lib
+from ._cabi import ST_EPI_F32OUT, ST_EPI_GEGLU, ST_EPI_SILU, ST_W_STATIC, check, lib
 
 BF16 = torch.bfloat16
 
@@ -181,8 +181,11 @@ SMALL_M = 32
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, activation: bool = False,
            residual: Optional[torch.Tensor] = None, geglu: bool = False, silu_input: bool = False,
-           block_n: int = 0, w_static: bool = False, gn_stats: int = 0):
+           block_n: int = 0, w_static: bool = False, gn_stats: int = 0, out: Optional[torch.Tensor] = None):
     """y = epi(x @ weight.T + bias) [+ residual]; weight is (N, K) as in nn.Linear.
+
+    out: optional preallocated bf16 result (rows of N contiguous elements with a uniform pitch, e.g. a row slice of a
+    larger buffer); not on the tiny-M path.
 
     gn_stats = rows per image (> 0): y feeds a GroupNorm -- also return the per-tile column statistics the GEMM epilogue
     can emit for free, as `(y, partials)`; partials is None when the shape does not allow it (see gn_partial_rows).
@@ -207,9 +210,18 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     wflag = ST_W_STATIC if w_static else 0
     xr, m, lda = _rows(x)
     n_out = n_rows // 2 if geglu else n_rows
-    out = torch.empty(x.shape[:-1] + (n_out,), dtype=BF16, device=x.device)
+    ldd = n_out
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (n_out,), dtype=BF16, device=x.device)
+    else:
+        _require_bf16_cuda("linear", out)
+        if out.shape[-1] != n_out or out.numel() != m * n_out or out.stride(-1) != 1:
+            raise ValueError(f"linear: out must hold {m} rows of {n_out} contiguous elements, got {tuple(out.shape)}")
+        orows, _, ldd = _rows(out)
+        if orows.data_ptr() != out.data_ptr():
+            raise ValueError("linear: out rows must have a uniform pitch")
     L = lib()
-    if m <= SMALL_M and not geglu and residual is None:
+    if m <= SMALL_M and not geglu and residual is None and ldd == n_out:
         check(L.st_linear_small_m_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias),
                                        out.data_ptr(), n_out, m, n_rows, k, int(silu_input), int(activation), wflag,
                                        _stream(x)), "linear_small_m")
@@ -227,9 +239,60 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     part = None
     if gn_stats and not geglu and gn_partial_rows(m, gn_stats):
         part = torch.empty((m // 128, n_out, 2), dtype=torch.float32, device=x.device)
-    check(L.st_gemm_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), out.data_ptr(), n_out, m, n_rows, k,
+    check(L.st_gemm_bf16(xr.data_ptr(), lda, weight.data_ptr(), weight.stride(0), out.data_ptr(), ldd, m, n_rows, k,
                          _ptr(bias), res_ptr, ldr, flags, block_n, _ptr(part), _stream(x)), "gemm")
     return (out, part) if gn_stats else out
+
+
+def matmul_nt_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fp32 (M, N) = a (M, K) @ b (N, K)^T on the tensor-core GEMM, fp32 result (ST_EPI_F32OUT): attention scores of a
+    head wider than the flash kernels cover (the VAE mid block: one head of 512), ahead of `softmax_rows`."""
+    _require_bf16_cuda("matmul_nt_f32", a, b)
+    _ensure_workspace(a.device)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError(f"matmul_nt_f32: expected (M, K) and (N, K), got {tuple(a.shape)} and {tuple(b.shape)}")
+    ar, m, lda = _rows(a)
+    br, n, ldb = _rows(b)
+    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    check(lib().st_gemm_bf16(ar.data_ptr(), lda, br.data_ptr(), ldb, out.data_ptr(), n, m, n, a.shape[1], 0, 0, 0,
+                             ST_EPI_F32OUT, 0, 0, _stream(a)), "gemm_f32out")
+    return out
+
+
+def softmax_rows(scores: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 softmax(scale * scores) over the last dimension of an fp32 (M, N) matrix."""
+    if scores.dtype != torch.float32 or scores.device.type != "cuda" or scores.dim() != 2 or scores.stride(1) != 1:
+        raise ValueError("softmax_rows: expected a 2-D fp32 CUDA tensor with contiguous rows")
+    m, n = scores.shape
+    if out is None:
+        out = torch.empty((m, n), dtype=BF16, device=scores.device)
+    check(lib().st_softmax_rows_f32_bf16(scores.data_ptr(), scores.stride(0), out.data_ptr(), out.stride(0), m, n,
+                                         float(scale), _stream(scores)), "softmax_rows")
+    return out
+
+
+def transpose_tokens(x: torch.Tensor) -> torch.Tensor:
+    """(B, T, C) -> dense (B, C, T): the B operand V^T of P @ V when P @ V runs on the plain GEMM."""
+    _require_bf16_cuda("transpose_tokens", x)
+    if x.dim() != 3 or x.stride(2) != 1 or x.stride(0) != x.shape[1] * x.stride(1):
+        x = x.contiguous()
+    b, t, c = x.shape
+    out = torch.empty((b, c, t), dtype=BF16, device=x.device)
+    check(lib().st_nhwc_to_nchw_bf16(x.data_ptr(), x.stride(1), out.data_ptr(), b, t, c, _stream(x)), "transpose_tokens")
+    return out
+
+
+def pointwise_conv_small(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], in_scale: float = 1.0) -> torch.Tensor:
+    """1x1 convolution between at most 8 channels on a dense NCHW tensor, input pre-scaled (the VAE's post_quant_conv)."""
+    _require_bf16_cuda("pointwise_conv_small", x, weight, bias)
+    x = x.contiguous()
+    n, ci, h, w = x.shape
+    co = weight.shape[0]
+    wm = weight.reshape(co, ci).contiguous()
+    out = torch.empty((n, co, h, w), dtype=BF16, device=x.device)
+    check(lib().st_pointwise_conv_small_bf16(x.data_ptr(), wm.data_ptr(), _ptr(bias), out.data_ptr(), n, h * w, ci, co,
+                                             float(in_scale), _stream(x)), "pointwise_conv_small")
+    return out
 
 
 def sdxl_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], activation: bool) -> torch.Tensor:

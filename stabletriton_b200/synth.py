@@ -92,14 +92,14 @@ def synth_state_dict(module_on_meta: torch.nn.Module, seed: int = 0, device="cpu
     return sd
 
 
-def build_unet(cfg=None, seed: int = 0, device="cuda", dtype=torch.bfloat16):
+def build_unet(cfg=None, seed: int = 0, device="cuda", dtype=torch.bfloat16, adm_input: bool = False):
     """A `UNet2DConditionModel` with synthetic weights, built on the meta device (no default-init cost)
     and materialised directly on `device`; values are generated in fp32 and rounded once to `dtype`."""
     from .unet import UNet2DConditionModel, UNetConfig
 
     cfg = cfg or UNetConfig.sdxl()
     with torch.device("meta"):
-        model = UNet2DConditionModel(cfg)
+        model = UNet2DConditionModel(cfg, adm_input=adm_input)
     sd = synth_state_dict(model, seed=seed, device=device, dtype=dtype)
     model.load_state_dict(sd, strict=True, assign=True)
     for p in model.parameters():

@@ -312,10 +312,14 @@ class UNet2DConditionModel(nn.Module):
     """forward(sample, timesteps, encoder_hidden_states, added_cond_kwargs, **kwargs) -> [eps]
     (list-valued, so `unet(...)[0]` works in a Diffusers pipeline; reference: unet_pt.py:469-542)."""
 
-    def __init__(self, cfg: Optional[UNetConfig] = None):
+    def __init__(self, cfg: Optional[UNetConfig] = None, adm_input: bool = False):
         super().__init__()
         cfg = cfg or UNetConfig.sdxl()
         self.cfg = cfg
+        # adm_input: the micro-conditioning arrives already embedded, as ComfyUI / sgm pass it (`y` = [pooled text |
+        # Fourier features of the size / crop ids], add_embed_in_dim wide) under added_cond_kwargs["adm"]; the
+        # `add_time_proj` embedding of `time_ids` is then not part of the graph (stabletriton_b200/comfy.py)
+        self.adm_input = bool(adm_input)
         # what a Diffusers pipeline reads from `unet.config` (reference: unet_pt.py:420-428)
         self.config = make_config_shim(cfg)
 
@@ -353,10 +357,13 @@ class UNet2DConditionModel(nn.Module):
         timesteps = timesteps.expand(sample.shape[0])
         emb = self.time_embedding(self.time_proj(timesteps).to(dtype=sample.dtype))
 
-        text_embeds = added_cond_kwargs.get("text_embeds")
-        time_ids = added_cond_kwargs.get("time_ids")
-        time_embeds = self.add_time_proj(time_ids.flatten()).reshape((text_embeds.shape[0], -1))
-        add_embeds = torch.concat([text_embeds, time_embeds], dim=-1).to(emb.dtype)
+        if self.adm_input:
+            add_embeds = added_cond_kwargs.get("adm").to(emb.dtype)
+        else:
+            text_embeds = added_cond_kwargs.get("text_embeds")
+            time_ids = added_cond_kwargs.get("time_ids")
+            time_embeds = self.add_time_proj(time_ids.flatten()).reshape((text_embeds.shape[0], -1))
+            add_embeds = torch.concat([text_embeds, time_embeds], dim=-1).to(emb.dtype)
         emb = emb + self.add_embedding(add_embeds)
 
         sample = self.conv_in(sample)
