@@ -57,12 +57,35 @@ def attach_engine(pipe, engine_unet=None, **build_kwargs):
     return pipe
 
 
+def attach_vae(pipe, device="cuda", dtype=torch.bfloat16):
+    """Optional: decode on the B200 kernels too (the reference leaves the pipeline's eager VAE in place).
+    The pipeline keeps calling `pipe.vae.decode(latents / scaling_factor, return_dict=False)[0]`."""
+    from stabletriton_b200.vae import AutoencoderKLDecoder, VAEConfig, compile_vae
+
+    cfg = VAEConfig(scaling_factor=float(pipe.vae.config.scaling_factor))
+    dec = AutoencoderKLDecoder(cfg).to(dtype).to(device)
+    dec.load_state_dict({k: v.to(device=device, dtype=dtype) for k, v in pipe.vae.state_dict().items()
+                         if k.startswith(("decoder.", "post_quant_conv."))}, strict=True)
+    engine = compile_vae(dec.eval().requires_grad_(False))
+
+    def decode(z, return_dict: bool = True, **_):
+        image = engine.decode(z.to(dtype), pre_scaled=True)
+        if not return_dict:
+            return (image,)
+        from diffusers.models.autoencoders.vae import DecoderOutput  # only reached inside a Diffusers process
+        return DecoderOutput(sample=image)
+
+    pipe.vae.decode = decode
+    return pipe
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="stabilityai/stable-diffusion-xl-base-1.0")
     ap.add_argument("--prompt", default="a photo of an astronaut riding a horse on mars")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--out", default="sdxl_b200.png")
+    ap.add_argument("--engine-vae", action="store_true", help="also run the VAE decode on the B200 kernels")
     args = ap.parse_args()
     try:
         from diffusers import DiffusionPipeline  # third party; not installed in the build image
@@ -72,6 +95,8 @@ def main():
 
     pipe = DiffusionPipeline.from_pretrained(args.model, torch_dtype=torch.bfloat16, use_safetensors=True).to("cuda")
     attach_engine(pipe)
+    if args.engine_vae:
+        attach_vae(pipe)
 
     image = pipe(args.prompt, num_inference_steps=args.steps).images[0]  # warm-up: kernels loaded, CUDA graph captured
     del image

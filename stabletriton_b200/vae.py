@@ -213,7 +213,7 @@ class CompiledVAEDecoder:
         qkv = K.linear(tok, self._wqkv, self._bqkv, w_static=True)  # (b, t, 3c)
         q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
         vt = K.transpose_tokens(v)                              # (b, c, t): the B operand of P @ V
-        o = torch.empty((b, t, c), dtype=torch.bfloat16, device=x.device)
+        o = torch.empty((b, t, c), dtype=x.dtype, device=x.device)
         scale = 1.0 / math.sqrt(c)
         for i in range(b):
             for r0 in range(0, t, self.ATTN_ROWS):
@@ -224,9 +224,10 @@ class CompiledVAEDecoder:
         y, yp = K.linear(o, att.to_out[0].weight, att.to_out[0].bias, residual=res, w_static=True, gn_stats=t)
         return y.reshape(b, h, w, c).permute(0, 3, 1, 2), yp
 
-    def _forward(self, latents: torch.Tensor) -> torch.Tensor:
+    def _forward(self, latents: torch.Tensor, pre_scaled: bool = False) -> torch.Tensor:
         m, d = self.model, self.model.decoder
-        z = K.pointwise_conv_small(latents, m.post_quant_conv.weight, m.post_quant_conv.bias, 1.0 / self.cfg.scaling_factor)
+        z = K.pointwise_conv_small(latents, m.post_quant_conv.weight, m.post_quant_conv.bias,
+                                   1.0 if pre_scaled else 1.0 / self.cfg.scaling_factor)
         x, part = K.conv2d(z, d.conv_in.weight, d.conv_in.bias, w_static=True, gn_stats=True)
         x, part = self._resnet(x, part, d.mid_block.resnets[0])
         x, part = self._attention(x, part, d.mid_block.attentions[0])
@@ -241,9 +242,9 @@ class CompiledVAEDecoder:
         return K.conv2d(x, d.conv_out.weight, d.conv_out.bias, nchw_output=True, w_static=True)
 
     @torch.no_grad()
-    def eager_decode(self, latents: torch.Tensor) -> torch.Tensor:
+    def eager_decode(self, latents: torch.Tensor, pre_scaled: bool = False) -> torch.Tensor:
         """The launch sequence on the current stream, no graph."""
-        return self._forward(self._check(latents))
+        return self._forward(self._check(latents), pre_scaled)
 
     def _check(self, latents):
         if latents.device.type != "cuda" or latents.dtype != torch.bfloat16 or latents.dim() != 4 \
@@ -253,11 +254,13 @@ class CompiledVAEDecoder:
         return latents.contiguous()
 
     @torch.no_grad()
-    def decode(self, latents: torch.Tensor) -> torch.Tensor:
+    def decode(self, latents: torch.Tensor, pre_scaled: bool = False) -> torch.Tensor:
+        """pre_scaled: `latents` have already been divided by the scaling factor, as a Diffusers pipeline does before it
+        calls `vae.decode` (pipeline_stable_diffusion_xl.py: `self.vae.decode(latents / self.vae.config.scaling_factor)`)."""
         latents = self._check(latents)
         if not self.cuda_graph:
-            return self._forward(latents)
-        key = (tuple(latents.shape), latents.device.index)
+            return self._forward(latents, pre_scaled)
+        key = (tuple(latents.shape), latents.device.index, bool(pre_scaled))
         hit = self._graphs.get(key)
         if hit is None:
             static_in = latents.clone()
@@ -265,11 +268,11 @@ class CompiledVAEDecoder:
             side.wait_stream(torch.cuda.current_stream(latents.device))
             with torch.cuda.stream(side):
                 for _ in range(2):  # lazy initialisation (padded conv_in / conv_out operands, workspace) stays out of the capture
-                    self._forward(static_in)
+                    self._forward(static_in, pre_scaled)
                 torch.cuda.synchronize(latents.device)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
-                    static_out = self._forward(static_in)
+                    static_out = self._forward(static_in, pre_scaled)
             torch.cuda.synchronize(latents.device)
             hit = (graph, static_in, static_out)
             self._graphs[key] = hit

@@ -56,8 +56,11 @@ def layer_norm(x, weight, bias, eps):
 
 
 def linear(x, weight, bias=None, activation=False, residual=None, geglu=False, silu_input=False, block_n=0,
-           w_static=False, gn_stats=0):
+           w_static=False, gn_stats=0, out=None):
     _count("linear_geglu" if geglu else "linear")
+    if out is not None:
+        out.copy_(linear(x, weight, bias, activation, residual, geglu, silu_input))
+        return out
     if silu_input:
         x = F.silu(x)
     y = F.linear(x, weight, bias)
@@ -110,6 +113,28 @@ def conv2d(x, weight, bias, stride=1, padding=1, temb=None, residual=None, nchw_
     return y
 
 
+def matmul_nt_f32(a, b):
+    _count("matmul_nt_f32")
+    return a.float() @ b.float().t()
+
+
+def softmax_rows(scores, scale, out=None):
+    _count("softmax_rows")
+    assert scores.dtype == torch.float32
+    p = torch.softmax(scores * scale, dim=-1)
+    return p if out is None else out.copy_(p)
+
+
+def transpose_tokens(x):
+    _count("transpose_tokens")
+    return x.transpose(1, 2).contiguous()
+
+
+def pointwise_conv_small(x, weight, bias, in_scale=1.0):
+    _count("pointwise_conv_small")
+    return F.conv2d(x * in_scale, weight, bias)
+
+
 def concat_channels(a, b):
     _count("concat")
     return torch.cat([a, b], dim=1)
@@ -125,7 +150,8 @@ def timestep_embedding(t, num_channels):
 
 
 _NAMES = ["groupnorm_wrapper", "layer_norm", "linear", "geglu_wrapper", "attention_btc", "upsample_nearest2x",
-          "conv2d", "concat_channels", "timestep_embedding"]
+          "conv2d", "concat_channels", "timestep_embedding", "matmul_nt_f32", "softmax_rows", "transpose_tokens",
+          "pointwise_conv_small"]
 
 
 @contextlib.contextmanager

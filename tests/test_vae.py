@@ -63,6 +63,30 @@ def test_model_definition_matches_oracle_fp32(cfg_name, hw):
     assert rel <= 1e-5, (rel, cos)
 
 
+def test_kernel_path_composition_with_the_eager_test_double():
+    """The launch sequence of CompiledVAEDecoder (which producer feeds which GroupNorm its statistics, the q / k / v
+    slices of the fused projection, score blocks of ATTN_ROWS query rows written into row slices of the output) run on
+    the CPU with tests/fake_kernels.py standing in for the CUDA kernels: must reproduce the model definition."""
+    import fake_kernels
+    from stabletriton_b200.vae import CompiledVAEDecoder, VAEConfig, build_vae_decoder
+    cfg = VAEConfig.tiny()
+    model = build_vae_decoder(cfg, seed=5, device="cpu", dtype=torch.float32)
+    z = _latents(2, 16, seed=9)
+    vae = CompiledVAEDecoder.__new__(CompiledVAEDecoder)  # no device / dtype gate: this is the CPU double
+    vae.model, vae.cfg, vae.cuda_graph, vae._graphs = model, cfg, False, {}
+    att = model.decoder.mid_block.attentions[0]
+    vae._wqkv = torch.cat([att.to_q.weight, att.to_k.weight, att.to_v.weight], dim=0)
+    vae._bqkv = torch.cat([att.to_q.bias, att.to_k.bias, att.to_v.bias], dim=0)
+    vae.ATTN_ROWS = 96  # 256 tokens -> three score blocks, the last one ragged
+    with torch.no_grad(), fake_kernels.installed() as calls:
+        got = vae._forward(z)
+        pre = vae._forward(z / cfg.scaling_factor, pre_scaled=True)
+        ref = model(z)
+    assert parity(got, ref)[0] <= 1e-5 and parity(pre, ref)[0] <= 1e-5
+    assert calls["softmax_rows"] == 2 * 2 * 3 and calls["matmul_nt_f32"] == 12 and calls["pointwise_conv_small"] == 2
+    assert calls["groupnorm_from_partials"] >= 10  # the fake GroupNorm verifies every set of partials it is handed
+
+
 def test_compile_vae_refuses_cpu_models():
     from stabletriton_b200.vae import VAEConfig, build_vae_decoder, compile_vae
     model = build_vae_decoder(VAEConfig.tiny(), device="cpu", dtype=torch.bfloat16)
