@@ -501,6 +501,264 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Resident variant for K/V sweeps whose tile count is a few per SM (self-attention at T = 1024, CFG batch 2: 320 query
+// tiles on 148 SMs): the short kernel's footprint (128 TMEM columns, 160 threads) with a loop over 64-key blocks, THREE
+// CTAs resident per SM (measured: the launch time steps between 444 and 448 tiles).  Each CTA is a plain serial chain
+// (S -> softmax -> P.V per block, nothing overlapped inside the CTA); the overlap comes from the sibling CTAs, and --
+// the point -- every tile of such a launch is resident at once: the pipelined kernel below owns an SM, so 320 tiles
+// are 148 + 148 + 24, three rounds for 2.16 rounds of work (28 - 29 us against 25 - 26 us here).  Beyond 3 tiles per SM
+// the pipelined kernel wins (~725 against ~940 cycles per 128 x 64 block and SM); the launcher picks by tile count.
+//
+//   warp 0      TMA loads (Q once; K / V rings of kStages 64-row blocks) and both MMA batches
+//   warps 1-4   one query row per thread: the 64 scores of the block in registers, exact block max, lazy reference
+//               (moves when the max grows by more than 2^8; then O in TMEM and l are rescaled by this thread -- S(j)
+//               complete implies P(j-1).V(j-1) complete, both were issued by the same thread and one commit covers
+//               them), exponentials, bf16 P over the dead S columns
+//
+//   TMEM   S [0,64) fp32;  P [0,32) packed bf16, aliasing S;  O [64,128), accumulated over the whole sweep.
+//          P(j).V(j) and S(j+1) are issued back to back: tcgen05.mma executes in issue order, so S(j+1) overwrites
+//          the P(j) columns only after P(j).V(j) has read them.
+//
+// Block period of one CTA (clock64 stamps, selftest attn1 with ST_ATTN_IMPL=resident): ~1.75 k cycles = S in registers
+// 90 + max / reference 200 + 64 exponentials, sums, packs, P stores 730 + store wait / fence / arrive 90 + issuer wake-up
+// 45 + 8 MMAs and 2 commits issued 360 + execution, commit, wake-up 210.  Variants measured and dropped
+// (profiles/r02_attention_experiments.txt, section 8): two softmax warps per row, 32-key ping-pong S buffers, a
+// four-warp CTA whose warp 0 also issues, half of the exponentials on the FMA pipe, busy-polling waits.
+constexpr int kResKV = 64;
+constexpr int kResThreads = 160;
+constexpr int kResKVBytes = kResKV * kAttnD * 2;
+constexpr int kResTmemCols = 128;
+constexpr int kResStages = 2;
+constexpr int kResSmemBytes = kAttnTileBytes + 2 * kResStages * kResKVBytes + 256 + 1024;
+constexpr int kResCtasPerSm = 3;
+constexpr float kResTau = 8.f;  // log2 units: the row reference moves when the block max exceeds it by more than 2^8
+
+__global__ void __launch_bounds__(kResThreads, kResCtasPerSm)
+attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                         const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  constexpr int kStages = kResStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAttnTileBytes;
+  uint8_t* sV = sK + kStages * kResKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * kResKVBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* v_full = k_full + kStages;
+  uint64_t* kv_empty = v_full + kStages;
+  uint64_t* s_full = kv_empty + kStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kAttnBlockQ;
+  const int b = blockIdx.y / p.H;
+  const int h = blockIdx.y - b * p.H;
+  const int nkv = (p.Tk + kResKV - 1) / kResKV;
+#define RES_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) p.trace[slot] = clock64();            \
+  } while (0)
+  if (threadIdx.x == 0) RES_TRACE(0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);  // one arrival per softmax warp
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<kResTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // prologue above touched only shared / tensor memory
+  pdl_wait();
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_P = tmem_base;
+  const uint32_t tmem_O = tmem_base + 64;
+
+  if (warp == 0) {
+    // ===================================== TMA + MMA issue ==================================
+    auto load_kv = [&](int j) {  // lane 0 only
+      const int st = j % kStages;
+      mbar_expect_tx(&k_full[st], kResKVBytes);
+      tma_load_4d(sK + st * kResKVBytes, &tmap_k, &k_full[st], 0, j * kResKV, h, b);
+      mbar_expect_tx(&v_full[st], kResKVBytes);
+      tma_load_4d(sV + st * kResKVBytes, &tmap_v, &v_full[st], 0, j * kResKV, h, b);
+    };
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kAttnTileBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b);
+      for (int j = 0; j < kStages && j < nkv; ++j) load_kv(j);
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, kResKV, 0, 0);  // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kAttnD, 0, 1);  // P (TMEM)    x V (MN-major)
+    constexpr uint32_t kStep = kResKVBytes >> 4;                      // descriptor address units (16 bytes)
+    const uint64_t desc_q = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+    const uint64_t desc_k0 = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
+    const uint64_t desc_v0 = umma_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+    auto issue_s = [&](int j) {  // K(j) has landed (waited for by the caller, off the P -> S critical path)
+      const uint64_t dk = desc_k0 + static_cast<uint64_t>((j % kStages) * kStep);
+#pragma unroll
+      for (int k = 0; k < kAttnD / 16; ++k) umma_bf16_ss_elect(tmem_S, desc_q + 2 * k, dk + 2 * k, idesc_s, k != 0);
+      umma_commit_elect(s_full);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j % kStages;
+      const uint32_t ph = (j / kStages) & 1;
+      mbar_wait(&v_full[st], ph);
+      if (j + 1 < nkv) mbar_wait(&k_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
+      if (j == 4) RES_TRACE(8);
+      mbar_wait(p_full, j & 1);  // P(j) is in TMEM (and O has been rescaled if the row references moved)
+      tc_fence_after();
+      if (j == 4) RES_TRACE(9);
+      const uint64_t dv = desc_v0 + static_cast<uint64_t>(st * kStep);
+#pragma unroll
+      for (int kk = 0; kk < kResKV / 16; ++kk)  // 16 V rows (2 KB) per instruction
+        umma_bf16_ts_elect(tmem_O, tmem_P + kk * 8, dv + 128 * kk, idesc_o, (j > 0) || (kk != 0));
+      umma_commit_elect(&kv_empty[st]);
+      if (j + 1 < nkv)
+        issue_s(j + 1);
+      else
+        umma_commit_elect(o_full);
+      if (j == 4) RES_TRACE(10);
+      if (j + kStages < nkv) {  // refill the stage block j has just released
+        mbar_wait(&kv_empty[st], ph);
+        if (lane == 0) load_kv(j + kStages);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================== softmax ==========================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_s = tmem_S + lane_off;
+    const uint32_t t_p = tmem_P + lane_off;
+    const uint32_t t_o = tmem_O + lane_off;
+    float m = -INFINITY, l = 0.f;  // m: reference of my row (scaled scores, log2 domain)
+    for (int j = 0; j < nkv; ++j) {
+      const int valid = p.Tk - j * kResKV;  // columns >= valid are padding (K rows zero-filled by TMA)
+      if (j == 4 && warp == 1) RES_TRACE(1);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j == 4 && warp == 1) RES_TRACE(2);
+      if (j == 5 && warp == 1) RES_TRACE(12);
+      uint32_t s[64];
+      tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(s));
+      tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(s + 32));
+      tmem_ld_wait();
+      if (j == 4 && warp == 1) RES_TRACE(3);
+      if (valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf -> 2^(-inf) = 0
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        mx0 = max3f(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = max3f(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = max3f(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = max3f(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+      }
+      const float mj = max3f(mx0, mx1, fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0 commutes with max; column 0 is valid
+      const bool move = mj > m + kResTau;                                // always true on the first block (m = -inf)
+      const float m_new = move ? mj : m;
+      if (j > 0 && __any_sync(0xffffffffu, move)) {
+        const float f = ex2_approx(m - m_new);  // exactly 1 for rows that keep their reference
+        l *= f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(t_o + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st_32x32b_x16(t_o + c, *reinterpret_cast<const uint32_t(*)[16]>(o));
+          tmem_st_32x32b_x16(t_o + c + 16, *reinterpret_cast<const uint32_t(*)[16]>(o + 16));
+        }
+      }
+      m = m_new;
+      const float neg_m = -m;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      if (j == 4 && warp == 1) RES_TRACE(4);
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        float e[32];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          fma2_bcast(__uint_as_float(s[c + 2 * q]), __uint_as_float(s[c + 2 * q + 1]), p.scale_log2, neg_m, e[2 * q], e[2 * q + 1]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = ex2_approx_ordered(e[i]);
+        ready16(e, 0);
+        ready16(e, 16);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          add2_acc(rs0, rs1, e[i + 0], e[i + 1]);
+          add2_acc(rs2, rs3, e[i + 2], e[i + 3]);
+          pk[(i >> 1) + 0] = pack_bf16x2(e[i + 0], e[i + 1]);
+          pk[(i >> 1) + 1] = pack_bf16x2(e[i + 2], e[i + 3]);
+        }
+        tmem_st_32x32b_x16(t_p + (c >> 1), pk);
+      }
+      l += (rs0 + rs1) + (rs2 + rs3);
+      if (j == 4 && warp == 1) RES_TRACE(5);
+      tmem_st_wait();
+      if (j == 4 && warp == 1) RES_TRACE(6);
+      tc_fence_before();
+      warp_arrive(p_full, lane);
+      if (j == 4 && warp == 1) RES_TRACE(7);
+    }
+    const float inv = 1.f / l;
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    uint32_t o[64];
+    tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(o));
+    tmem_ld_32x32b_x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(o + 32));
+    tmem_ld_wait();
+    if (q0 + row < p.Tq) {
+      __nv_bfloat16* orow = p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        uint4 ov;
+        ov.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+        ov.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+        ov.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+        ov.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + i) = ov;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<kResTmemCols>(tmem_base);
+  if (threadIdx.x == 0) RES_TRACE(11);
+#undef RES_TRACE
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pipelined variant for Tk > 128 (self-attention): ONE CTA per SM that owns all 512 TMEM columns, so S and P
 // are double-buffered and O accumulates in TMEM across the whole K/V sweep; warp-specialised (warp numbers for the
 // 8-exp-warp layout, kParts = 2; with kParts = 4 the exp warps are 2-17 and the rest follow):
@@ -1084,6 +1342,7 @@ static int g_attn_parts = 0;  // 0: not decided yet (ST_ATTN_PARTS or the defaul
 constexpr int kAttnDefaultPoly = 0;
 constexpr unsigned kAttnDefaultWaitHint = 1000, kAttnDefaultWaitSleep = 0;  // hint: T = 4096 622 -> 632 TFLOP/s (gpu_call25)
 static int g_attn_poly = -1;  // -1: not decided yet (ST_ATTN_POLY or the default)
+static int g_attn_impl = -1;  // -1: not decided yet (ST_ATTN_IMPL); 0: by shape; 1 two-CTA, 2 pipelined, 3 short, 4 resident
 
 }  // namespace st
 
@@ -1106,14 +1365,18 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   int rc = make_tmap_bhtd(&tq, q, B, H, Tq, q_sb, q_sh, q_st);
   if (rc != ST_OK) return rc;
   // one K/V block (cross-attention, Tk = 77): the short-context kernel (Tk <= 80) or the two-CTA-per-SM kernel
-  // (Tk <= 128); longer sweeps: the pipelined one
-  static const int force = [] {
-    const char* e = getenv("ST_ATTN_IMPL");  // debug: "2cta" / "pipelined" / "short"
-    return !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : (!strcmp(e, "short") ? 3 : 0)));
-  }();
-  const bool pipelined = (force == 1 || force == 2) ? force == 2 : Tk > kAttnBlockKV;
-  const bool short_kv = !pipelined && Tk <= kShortKV && force != 1;
-  const int kv_box = short_kv ? kShortKV : kAttnBlockKV;
+  // (Tk <= 128); longer sweeps: the resident kernel while every query tile of the launch fits on the machine at once
+  // (3 CTAs per SM), the pipelined one beyond that
+  if (g_attn_impl < 0) {
+    const char* e = getenv("ST_ATTN_IMPL");  // debug: "2cta" / "pipelined" / "short" / "resident"
+    g_attn_impl = !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : (!strcmp(e, "short") ? 3 : (!strcmp(e, "resident") ? 4 : 0))));
+  }
+  const int force = g_attn_impl;
+  const long long tiles = static_cast<long long>((Tq + kAttnBlockQ - 1) / kAttnBlockQ) * B * H;
+  const bool resident = force == 4 || (force == 0 && Tk > kAttnBlockKV && tiles <= static_cast<long long>(kResCtasPerSm) * device_sm_count());
+  const bool pipelined = !resident && ((force == 1 || force == 2) ? force == 2 : Tk > kAttnBlockKV);
+  const bool short_kv = !resident && !pipelined && Tk <= kShortKV && force != 1;
+  const int kv_box = resident ? kResKV : (short_kv ? kShortKV : kAttnBlockKV);
   rc = make_tmap_bhtd(&tk, k, B, H, Tk, k_sb, k_sh, k_st, kv_box);
   if (rc != ST_OK) return rc;
   rc = make_tmap_bhtd(&tv, v, B, H, Tk, v_sb, v_sh, v_st, kv_box);
@@ -1134,6 +1397,12 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
     cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(attn_fwd_short_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(attn_fwd_resident_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(attn_fwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return ST_ERR_CUDA;
+    }
     e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_fwd_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes);
@@ -1182,7 +1451,11 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   }();
   // the phase stamps, the polynomial share and the ablation switches exist in the 8-exp-warp layout only
   const int parts = (trace || g_attn_poly == 2 || ablate) ? 2 : g_attn_parts;
-  if (pipelined && parts == 4) {
+  if (resident) {
+    launch_kernel(attn_fwd_resident_kernel, dim3(grid), dim3(kResThreads), kResSmemBytes, static_cast<cudaStream_t>(stream),
+                  tq, tk, tv, p);
+    ST_CHECK_LAUNCH("attn_fwd_resident_kernel");
+  } else if (pipelined && parts == 4) {
     launch_kernel(attn_fwd_pipelined_kernel<false, 4>, dim3(grid), dim3(A3Layout<4>::kThreads), kA3SmemBytes,
                   static_cast<cudaStream_t>(stream), tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_pipelined_kernel");
@@ -1216,6 +1489,10 @@ void st_debug_set_attention_trace(void* buf) { st::g_attn_trace = static_cast<un
 // Debug / tuning hook: exp warps per TMEM lane quadrant of the pipelined kernel (2 or 4; 0 = back to the default).
 void st_debug_set_attention_parts(int parts) { st::g_attn_parts = (parts == 2 || parts == 4) ? parts : 0; }
 
+// Debug / test hook: force one of the kernels behind st_attention_bf16 (0 = by shape, 1 two-CTA, 2 pipelined, 3 short,
+// 4 resident; -1 = re-read ST_ATTN_IMPL).  Forcing a one-block kernel onto a longer K/V sweep is the caller's mistake.
+void st_debug_set_attention_impl(int impl) { st::g_attn_impl = (impl >= 0 && impl <= 4) ? impl : -1; }
+
 // Debug / tuning hook: element pairs out of every 8 whose exponential takes the FMA-pipe polynomial (0 or 2; -1 = default).
 void st_debug_set_attention_poly(int pairs) { st::g_attn_poly = (pairs == 0 || pairs == 2) ? pairs : -1; }
 
@@ -1233,6 +1510,9 @@ int st_debug_attention_occupancy(void) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, st::attn_fwd_kernel<false>, st::kAttnThreads, 0);
   printf("attn kernel: regs %d, static smem %zu, max dyn smem %d, local %zu, occupancy @%d B: %d, @48K: %d, @0: %d\n",
          fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, st::kAttnSmemBytes, n, n48, n0);
+  cudaFuncAttributes ra;
+  cudaFuncGetAttributes(&ra, st::attn_fwd_resident_kernel);
+  printf("resident kernel: regs %d, local %zu, dyn smem %d\n", ra.numRegs, ra.localSizeBytes, st::kResSmemBytes);
   return n;
 }
 

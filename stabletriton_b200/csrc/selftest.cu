@@ -765,6 +765,10 @@ int main(int argc, char** argv) {
                    atoi(argv[7]), true);
     return g_fail ? 1 : 0;
   }
+  if (!strcmp(what, "occ")) {  // registers / occupancy of the attention kernels
+    st_debug_attention_occupancy();
+    return 0;
+  }
   if (!strcmp(what, "attn1") && argc >= 6) {  // selftest attn1 B H Tq Tk
     unsigned long long* tr;
     CK(cudaMalloc(&tr, 64 * 8));
@@ -779,6 +783,13 @@ int main(int argc, char** argv) {
                           "reference read", "-", "-", "exp stream done (64 columns)", "p_full arrived",
                           "mma: p_full(2) seen", "mma: P(2).V(2) issued", "exp warp, last block: before wait",
                           "cta exit", "max warp: m(2) published", "max warp: m(3) published"};
+    if (getenv("ST_ATTN_IMPL") && !strcmp(getenv("ST_ATTN_IMPL"), "resident")) {
+      // resident kernel, block 4 of CTA (0,0): 1 softmax warp before the s_full wait, 2 S seen, 3 S in registers, 4 reference
+      // known, 5 exponentials + P stores issued, 6 stores complete, 7 p_full arrived; issuer: 8 before the p_full wait,
+      // 9 P seen, 10 P.V + next S issued; 12 softmax warp sees S(5); 11 CTA exit
+      for (int i = 1; i < 13; ++i)
+        if (h[i]) printf("  resident slot %2d  %8lld  (+%lld since slot 1)\n", i, (long long)(h[i] - h[0]), (long long)(h[i] - h[1]));
+    } else
     for (int i = 1; i < 14; ++i)
       if (h[i]) printf("  %-42s %8lld\n", nm[i], (long long)(h[i] - h[0]));
     if (h[16]) {

@@ -180,6 +180,33 @@ def test_attention_reference_moves(K, tk, growth):
     check(got.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
 
 
+@pytest.mark.parametrize("impl", [2, 4], ids=["pipelined", "resident"])
+@pytest.mark.parametrize("b,h,tq,tk,growth", [(2, 20, 1024, 1024, 0.0), (1, 3, 200, 333, 0.0), (1, 2, 256, 1024, 24.0),
+                                               (1, 2, 256, 1000, -0.9), (2, 3, 130, 129, 6.0), (1, 2, 100, 65, 0.0),
+                                               (1, 38, 1024, 512, 0.0), (2, 2, 4096, 2048, 3.0)])
+def test_attention_sweep_kernels_forced(K, impl, b, h, tq, tk, growth):
+    """st_attention_bf16 sends a K/V sweep (Tk > 128) to the resident kernel while all query tiles fit on the machine at
+    once (3 CTAs per SM) and to the pipelined kernel beyond that; here both are forced onto the same inputs, small and
+    large, with moving / never-moving softmax references and ragged tails.  Same arithmetic per element but different
+    block sizes (64 / 128 keys), so they agree within rounding, not bit for bit."""
+    from stabletriton_b200 import _cabi
+    L = _cabi._load()
+    q, k, v = rnd(b, tq, h * 64, seed=61) * 1.5, rnd(b, tk, h * 64, seed=62) * 1.5, rnd(b, tk, h * 64, seed=63)
+    if growth:
+        ramp = (1.0 + growth * torch.arange(tk, dtype=torch.float32) / tk).view(1, tk, 1)
+        k = (k.float() * ramp).to(torch.bfloat16)
+    ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
+    try:
+        L.st_debug_set_attention_impl(impl)
+        got = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+        again = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        L.st_debug_set_attention_impl(0)
+    check(got.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
+    assert torch.equal(got, again)
+
+
 def test_attention_long_sweep(K):
     """T = 16384 (the 2048^2 self-attention of SURVEY 8d config 5) against fp32 softmax(QK^T)V on the GPU, one head."""
     b, h, t = 1, 1, 16384
@@ -501,6 +528,7 @@ def test_attention_polynomial_exp2_share(K):
     q, k, v = rnd(b, tq, h * 64, seed=50) * 2.0, rnd(b, tk, h * 64, seed=51) * 2.0, rnd(b, tk, h * 64, seed=52)
     ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
     try:
+        L.st_debug_set_attention_impl(2)
         L.st_debug_set_attention_parts(2)  # the polynomial share exists in the 8-exp-warp layout
         L.st_debug_set_attention_poly(0)
         base = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
@@ -510,6 +538,7 @@ def test_attention_polynomial_exp2_share(K):
     finally:
         L.st_debug_set_attention_poly(-1)
         L.st_debug_set_attention_parts(0)
+        L.st_debug_set_attention_impl(0)
     check(poly.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
     rel, cos = parity(poly.float(), base.float())
     assert rel <= 8e-3 and cos >= 0.99999, (rel, cos)
@@ -525,6 +554,7 @@ def test_attention_four_exp_warps_per_quadrant(K, b, h, tq, tk):
     q, k, v = rnd(b, tq, h * 64, seed=40), rnd(b, tk, h * 64, seed=41), rnd(b, tk, h * 64, seed=42)
     ref = O.attention_core(q.float(), k.float(), v.float(), h, 64)
     try:
+        L.st_debug_set_attention_impl(2)
         L.st_debug_set_attention_parts(2)
         two = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
         L.st_debug_set_attention_parts(4)
@@ -532,6 +562,7 @@ def test_attention_four_exp_warps_per_quadrant(K, b, h, tq, tk):
         torch.cuda.synchronize()
     finally:
         L.st_debug_set_attention_parts(0)
+        L.st_debug_set_attention_impl(0)
     check(four.cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
     rel, cos = parity(four.float(), two.float())
     assert rel <= 4e-3, (rel, cos)  # the row sum is accumulated in a different order (4 partial sums instead of 2)
