@@ -1335,6 +1335,21 @@ static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int 
   return ST_OK;
 }
 
+// Which kernel for a K/V sweep (Tk > 128)?  Cycle model calibrated on B200 (profiles/r02_attention_experiments.txt, 8):
+// the pipelined kernel owns an SM -- rounds of `sms` tiles, ~1.45 k cycles per 128-key block + ~7 k of prologue / tail per
+// round; the resident kernel holds up to three tiles per SM at once -- a 64-key block costs a CTA ~1.75 k cycles alone and
+// ~535 more per sibling CTA on its SM, an SM finishes one every ~940 cycles when it is full, + ~8.6 k once.  So the
+// resident kernel takes the short sweeps of more than two tiles per SM (T = 1024 self-attention: 320 tiles 28.4 -> 25.8 us,
+// 640 tiles 48 -> 42 us), the pipelined one the long sweeps (T >= 4096) and the launches of one or two rounds.
+static bool sweep_prefers_resident(long long tiles, int Tk, int sms) {
+  const long long rounds = (tiles + sms - 1) / sms;
+  const long long blocks128 = (Tk + kAttnBlockKV - 1) / kAttnBlockKV, blocks64 = (Tk + kResKV - 1) / kResKV;
+  const long long pipelined = rounds * (blocks128 * 1450 + 7000);
+  const long long siblings = (rounds < kResCtasPerSm ? rounds : kResCtasPerSm) - 1;
+  const long long chain = blocks64 * (1750 + 535 * siblings), throughput = tiles * blocks64 * 940 / sms;
+  return (chain > throughput ? chain : throughput) + 8600 < pipelined;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static unsigned long long* g_attn_trace = nullptr;
 constexpr int kAttnDefaultParts = 4;  // 16 exp warps: -0.16 ms on the attention launches of a step (gpu_call19)
@@ -1373,7 +1388,7 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   }
   const int force = g_attn_impl;
   const long long tiles = static_cast<long long>((Tq + kAttnBlockQ - 1) / kAttnBlockQ) * B * H;
-  const bool resident = force == 4 || (force == 0 && Tk > kAttnBlockKV && tiles <= static_cast<long long>(kResCtasPerSm) * device_sm_count());
+  const bool resident = force == 4 || (force == 0 && Tk > kAttnBlockKV && sweep_prefers_resident(tiles, Tk, device_sm_count()));
   const bool pipelined = !resident && ((force == 1 || force == 2) ? force == 2 : Tk > kAttnBlockKV);
   const bool short_kv = !resident && !pipelined && Tk <= kShortKV && force != 1;
   const int kv_box = resident ? kResKV : (short_kv ? kShortKV : kAttnBlockKV);
