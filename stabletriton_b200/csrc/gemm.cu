@@ -112,7 +112,7 @@ static TileChoice choose_tile(int M, int n_cols, bool geglu, int K, bool allow_p
 
 template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = false, bool kCluster = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdt,
-                       const GemmParams& p, cudaStream_t stream) {
+                       const CUtensorMap& tr, const CUtensorMap& trt, const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES, kCluster>;
   auto kernel = gemm_bf16_tc_kernel<BLOCK_N, STAGES, kConvA, kGeglu, kStreamK, kCluster>;
   static PerDeviceOnce configured;  // per instantiation AND per device (function attributes live in the context)
@@ -138,36 +138,37 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     const int pair_tiles = tiles / 2;
     grid = 2 * (pair_tiles < sms / 2 ? pair_tiles : sms / 2);
   }
-  launch_kernel_cluster(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, kCluster ? 2 : 1, ta, tb, td, tdt, p);
+  launch_kernel_cluster(kernel, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, kCluster ? 2 : 1, ta, tb, td, tdt, tr, trt, p);
   ST_CHECK_LAUNCH("gemm_bf16_tc_kernel");
   return ST_OK;
 }
 
 template <bool kConvA>
 static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdt,
-                         const GemmParams& p, int block_n, bool geglu, cudaStream_t stream) {
+                         const CUtensorMap& tr, const CUtensorMap& trt, const GemmParams& p, int block_n, bool geglu,
+                         cudaStream_t stream) {
   if (p.cluster) {
-    if (geglu && block_n == 256) return launch_gemm<256, 6, kConvA, true, false, true>(ta, tb, td, tdt, p, stream);
-    if (!geglu && block_n == 256) return launch_gemm<256, 6, kConvA, false, false, true>(ta, tb, td, tdt, p, stream);
-    if (!geglu && block_n == 192) return launch_gemm<192, 7, kConvA, false, false, true>(ta, tb, td, tdt, p, stream);
-    if (!geglu && block_n == 160) return launch_gemm<160, 7, kConvA, false, false, true>(ta, tb, td, tdt, p, stream);
+    if (geglu && block_n == 256) return launch_gemm<256, 6, kConvA, true, false, true>(ta, tb, td, tdt, tr, trt, p, stream);
+    if (!geglu && block_n == 256) return launch_gemm<256, 6, kConvA, false, false, true>(ta, tb, td, tdt, tr, trt, p, stream);
+    if (!geglu && block_n == 192) return launch_gemm<192, 7, kConvA, false, false, true>(ta, tb, td, tdt, tr, trt, p, stream);
+    if (!geglu && block_n == 160) return launch_gemm<160, 7, kConvA, false, false, true>(ta, tb, td, tdt, tr, trt, p, stream);
     set_error("gemm: no cluster instantiation for block_n %d", block_n);
     return ST_ERR_INVALID_ARGUMENT;
   }
   if (geglu) {
     switch (block_n) {
-      case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, td, tdt, p, stream);
-      case 128: return launch_gemm<128, 6, kConvA, true>(ta, tb, td, tdt, p, stream);
+      case 256: return launch_gemm<256, 4, kConvA, true>(ta, tb, td, tdt, tr, trt, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, true>(ta, tb, td, tdt, tr, trt, p, stream);
     }
   } else {
     switch (block_n) {
       case 256:
-        if (p.stream_k) return launch_gemm<256, 4, kConvA, false, true>(ta, tb, td, tdt, p, stream);
-        return launch_gemm<256, 4, kConvA, false>(ta, tb, td, tdt, p, stream);
-      case 192: return launch_gemm<192, 5, kConvA, false>(ta, tb, td, tdt, p, stream);
-      case 160: return launch_gemm<160, 5, kConvA, false>(ta, tb, td, tdt, p, stream);
-      case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, td, tdt, p, stream);
-      case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, td, tdt, p, stream);
+        if (p.stream_k) return launch_gemm<256, 4, kConvA, false, true>(ta, tb, td, tdt, tr, trt, p, stream);
+        return launch_gemm<256, 4, kConvA, false>(ta, tb, td, tdt, tr, trt, p, stream);
+      case 192: return launch_gemm<192, 5, kConvA, false>(ta, tb, td, tdt, tr, trt, p, stream);
+      case 160: return launch_gemm<160, 5, kConvA, false>(ta, tb, td, tdt, tr, trt, p, stream);
+      case 128: return launch_gemm<128, 6, kConvA, false>(ta, tb, td, tdt, tr, trt, p, stream);
+      case 64: return launch_gemm<64, 8, kConvA, false>(ta, tb, td, tdt, tr, trt, p, stream);
     }
   }
   set_error("gemm: unsupported block_n %d (0, 64, 128, 160, 192 or 256; GEGLU: 128 or 256)", block_n);
@@ -206,6 +207,15 @@ static bool want_stream_k(long tiles256, int nkb, long tiles_chosen, float** ws,
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ST_GEMM_RES_TMA=0: residual through per-thread row loads everywhere (A/B runs; the default is the TMA path)
+static bool res_tma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ST_GEMM_RES_TMA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 }  // namespace st
 
@@ -295,7 +305,15 @@ int st_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* D, int ld
   if (rc != ST_OK) return rc;
   rc = make_tmap_2d(&tdt, D, M, n_out, ldd_map, kGemmBlockM, 32, /*swizzle128=*/false);  // 32-column tail group of a 160-wide tile
   if (rc != ST_OK) return rc;
-  return dispatch_gemm<false>(ta, tb, td, tdt, p, block_n, geglu, static_cast<cudaStream_t>(stream));
+  CUtensorMap tr = td, trt = tdt;  // residual tile of a CTA's last output tile: same boxes as the store maps
+  p.res_tma = (residual && !out_f32 && !geglu && !p.stream_k && res_tma_enabled()) ? 1 : 0;
+  if (p.res_tma) {
+    rc = make_tmap_2d(&tr, residual, M, n_out, ldr, kGemmBlockM);
+    if (rc != ST_OK) return rc;
+    rc = make_tmap_2d(&trt, residual, M, n_out, ldr, kGemmBlockM, 32, /*swizzle128=*/false);
+    if (rc != ST_OK) return rc;
+  }
+  return dispatch_gemm<false>(ta, tb, td, tdt, tr, trt, p, block_n, geglu, static_cast<cudaStream_t>(stream));
 }
 
 int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int C, int K,
@@ -392,7 +410,15 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   if (rc != ST_OK) return rc;
   rc = make_tmap_2d(&tdt, y, M, K, K, kGemmBlockM, 32, /*swizzle128=*/false);
   if (rc != ST_OK) return rc;
-  return dispatch_gemm<true>(ta, tb, td, tdt, p, block_n, false, static_cast<cudaStream_t>(stream));
+  CUtensorMap tr = td, trt = tdt;
+  p.res_tma = (residual && !p.stream_k && res_tma_enabled()) ? 1 : 0;
+  if (p.res_tma) {
+    rc = make_tmap_2d(&tr, residual, M, K, K, kGemmBlockM);
+    if (rc != ST_OK) return rc;
+    rc = make_tmap_2d(&trt, residual, M, K, K, kGemmBlockM, 32, /*swizzle128=*/false);
+    if (rc != ST_OK) return rc;
+  }
+  return dispatch_gemm<true>(ta, tb, td, tdt, tr, trt, p, block_n, false, static_cast<cudaStream_t>(stream));
 }
 
 int st_set_workspace(void* ptr, size_t bytes) {

@@ -60,6 +60,8 @@ struct GemmParams {
   int spin_wait; // bit 0: the MMA warp polls full_bar (mbarrier.test_wait) instead of try_wait, bit 1: the producer polls
                  // empty_bar -- a suspended waiter is woken ~300 cycles late, and in a ring that is latency-bound
                  // (CTA pairs: 7 stages against a ~2850-cycle round trip) both waits block on every k-block
+  int res_tma;   // the residual tile of a CTA's LAST output tile arrives by TMA in the idle operand ring (host-side choice:
+                 // bf16 output, no GEGLU, no stream-K) instead of through per-thread row loads -- see the producer warp
   int drain_all; // debug (ST_GEMM_DRAIN=1): wait for the bulk stores' global writes before exit, not just their smem reads
   float* ws;            // [gridDim.x][128][BLOCK_N] fp32
   unsigned* flags;      // [gridDim.x], zero between launches (self-resetting)
@@ -130,6 +132,7 @@ template <int BLOCK_N, int STAGES, bool kConvA, bool kGeglu, bool kStreamK = fal
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d_tail,
+                    const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_r_tail,
                     const GemmParams p) {
   using S = GemmSmem<BLOCK_N, STAGES, kCluster>;
   constexpr int kAccCols = BLOCK_N;                       // fp32 accumulator columns per stage
@@ -150,7 +153,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;  // residual tile of the last output tile has landed in the ring
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
   float* s_bias = reinterpret_cast<float*>(s_out + S::kOutStageBytes + S::kBarrierBytes);  // [2][BLOCK_N]
   float* s_gn = s_bias + 2 * BLOCK_N;                                                      // [2][4][64][2]
 
@@ -209,6 +213,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], (kCluster ? 2 : 1) * kGemmEpiThreads / 32);  // pair: both CTAs' epilogue warps
     }
+    mbar_init(res_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -274,7 +279,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       const int cblocks = kConvA ? p.conv_C / kGemmBlockK : 1;
       int cursor = cursor0, tile, kb0, kb1;
+      int last_tile = -1;
       while (next_segment(cursor, tile, kb0, kb1)) {
+        last_tile = tile;
         const int m_blk = tile % p.num_m_blocks;
         const int n_blk = tile / p.num_m_blocks;
         const int m0 = m_blk * kGemmBlockM;
@@ -318,6 +325,32 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             phase ^= 1;
           }
         }
+      }
+      // Residual operand of this CTA's LAST tile (for the single-wave GEMMs -- out-projections and FF2 of every
+      // transformer block -- the only tile): no operand load follows, so the ring slots fall idle one by one while the
+      // last k-blocks are multiplied.  The residual tile goes, 64-column group by group, exactly where the epilogue will
+      // stage the output of that group (same 128-byte swizzle), as soon as the slots underneath have been released; the
+      // epilogue reads a chunk from there, adds, and writes the rounded result back in place.  The per-thread row loads
+      // this replaces (16 bytes per lane and request, 32 sectors per request) cost the main loop of the 2048 x 1280 x
+      // 1280 GEMM 2.8 k of its 9.7 k cycles: they compete with the operand stream for the SM's ingest.
+      constexpr int kOutColsP = kGeglu ? BLOCK_N / 2 : BLOCK_N;
+      constexpr int kGroupsP = (kOutColsP + 63) / 64;
+      constexpr bool kTailP = kOutColsP % 64 != 0;
+      if (!kStreamK && !kGeglu && p.res_tma && last_tile >= 0 &&
+          kGroupsP * S::kOutStageBytes <= STAGES * S::kStageBytes) {
+        constexpr int kResSlots = (kGroupsP * S::kOutStageBytes + S::kStageBytes - 1) / S::kStageBytes;
+        for (int sl = 0; sl < kResSlots; ++sl)  // as if the slot were loaded again: its last MMAs have retired
+          mbar_wait(&empty_bar[sl], (sl >= stage ? phase : phase ^ 1) ^ 1);
+        const int m0 = (last_tile % p.num_m_blocks) * kGemmBlockM;
+        const int n0 = (last_tile / p.num_m_blocks) * kOutColsP;
+        uint32_t bytes = 0;
+        for (int g = 0; g < kGroupsP; ++g)
+          if (n0 + g * 64 < p.n_out) bytes += (kTailP && g == kGroupsP - 1) ? kGemmBlockM * 32 * 2 : S::kOutStageBytes;
+        mbar_expect_tx(res_bar, bytes);
+        for (int g = 0; g < kGroupsP; ++g)
+          if (n0 + g * 64 < p.n_out)
+            tma_load_2d(smem_ab + g * S::kOutStageBytes, (kTailP && g == kGroupsP - 1) ? &tmap_r_tail : &tmap_r, res_bar,
+                        n0 + g * 64, m0);
       }
     }
   } else if (warp == 1) {
@@ -469,7 +502,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // (2) prefetch this thread's residual columns into registers while the main loop is still running
       uint4 res[kGroups * 4];
       const bool has_res = p.residual != nullptr && row_ok;
-      if (has_res) {
+      const bool res_smem = !kGeglu && ring_staging && p.res_tma != 0;  // the producer warp fetches the tile into the ring
+      if (has_res && !res_smem) {
         const __nv_bfloat16* res_row = p.residual + static_cast<size_t>(row) * p.ldr + n0 + half * 32;
 #pragma unroll
         for (int g = 0; g < kGroups; ++g)
@@ -483,6 +517,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // (3) accumulator ready
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (res_smem && p.residual != nullptr) mbar_wait(res_bar, 0);
       if (first_seg && warp == 2 && lane == 0) ST_TRACE(4);
       const uint32_t t_row = t_row0;
       int sk_last = blockIdx.x;  // contributors are CTAs blockIdx.x + 1 .. sk_last
@@ -576,7 +611,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; j += 8)
             if (n0 + c + j < p.n_out) {
-              const uint4 r4 = res[g * 4 + j / 8];
+              const uint4 r4 =
+                  !res_smem ? res[g * 4 + j / 8]
+                            : *reinterpret_cast<const uint4*>(
+                                  tail ? s_stage + tile_row * 64 + ((j >> 3) << 4)
+                                       : s_stage + tile_row * 128 + (((half * 4 + (j >> 3)) ^ (tile_row & 7)) << 4));
               const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {

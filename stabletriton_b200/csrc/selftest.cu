@@ -684,7 +684,7 @@ int main(int argc, char** argv) {
     __nv_bfloat16* A = dev_bf16((size_t)M * K, 1.0f);
     __nv_bfloat16* W = dev_bf16((size_t)N * K, 0.05f);
     __nv_bfloat16* b = dev_bf16(N, 0.5f);
-    __nv_bfloat16* r = dev_bf16((size_t)M * n_out, 1.0f);
+    __nv_bfloat16* r = (argc > 7 && !atoi(argv[7])) ? nullptr : dev_bf16((size_t)M * n_out, 1.0f);  // [res: 1 (default) / 0]
     __nv_bfloat16* D;
     CK(cudaMalloc(&D, (size_t)M * n_out * 2));
     unsigned long long* tr;
