@@ -1384,11 +1384,12 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   // (3 CTAs per SM), the pipelined one beyond that
   if (g_attn_impl < 0) {
     const char* e = getenv("ST_ATTN_IMPL");  // debug: "2cta" / "pipelined" / "short" / "resident"
-    g_attn_impl = !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : (!strcmp(e, "short") ? 3 : (!strcmp(e, "resident") ? 4 : 0))));
+    g_attn_impl = !e ? 0 : (!strcmp(e, "2cta") ? 1 : (!strcmp(e, "pipelined") ? 2 : (!strcmp(e, "short") ? 3 : (!strcmp(e, "resident") ? 4 : (!strcmp(e, "noresident") ? 5 : 0)))));
   }
-  const int force = g_attn_impl;
+  const bool no_resident = g_attn_impl == 5;  // A/B runs: choose by shape as before the resident kernel existed
+  const int force = no_resident ? 0 : g_attn_impl;
   const long long tiles = static_cast<long long>((Tq + kAttnBlockQ - 1) / kAttnBlockQ) * B * H;
-  const bool resident = force == 4 || (force == 0 && Tk > kAttnBlockKV && sweep_prefers_resident(tiles, Tk, device_sm_count()));
+  const bool resident = force == 4 || (force == 0 && !no_resident && Tk > kAttnBlockKV && sweep_prefers_resident(tiles, Tk, device_sm_count()));
   const bool pipelined = !resident && ((force == 1 || force == 2) ? force == 2 : Tk > kAttnBlockKV);
   const bool short_kv = !resident && !pipelined && Tk <= kShortKV && force != 1;
   const int kv_box = resident ? kResKV : (short_kv ? kShortKV : kAttnBlockKV);
@@ -1505,8 +1506,8 @@ void st_debug_set_attention_trace(void* buf) { st::g_attn_trace = static_cast<un
 void st_debug_set_attention_parts(int parts) { st::g_attn_parts = (parts == 2 || parts == 4) ? parts : 0; }
 
 // Debug / test hook: force one of the kernels behind st_attention_bf16 (0 = by shape, 1 two-CTA, 2 pipelined, 3 short,
-// 4 resident; -1 = re-read ST_ATTN_IMPL).  Forcing a one-block kernel onto a longer K/V sweep is the caller's mistake.
-void st_debug_set_attention_impl(int impl) { st::g_attn_impl = (impl >= 0 && impl <= 4) ? impl : -1; }
+// 4 resident, 5 = by shape without the resident kernel; -1 = re-read ST_ATTN_IMPL).  Forcing a one-block kernel onto a longer K/V sweep is the caller's mistake.
+void st_debug_set_attention_impl(int impl) { st::g_attn_impl = (impl >= 0 && impl <= 5) ? impl : -1; }
 
 // Debug / tuning hook: element pairs out of every 8 whose exponential takes the FMA-pipe polynomial (0 or 2; -1 = default).
 void st_debug_set_attention_poly(int pairs) { st::g_attn_poly = (pairs == 0 || pairs == 2) ? pairs : -1; }
