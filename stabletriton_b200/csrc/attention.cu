@@ -1505,6 +1505,12 @@ void st_debug_set_attention_trace(void* buf) { st::g_attn_trace = static_cast<un
 // Debug / tuning hook: exp warps per TMEM lane quadrant of the pipelined kernel (2 or 4; 0 = back to the default).
 void st_debug_set_attention_parts(int parts) { st::g_attn_parts = (parts == 2 || parts == 4) ? parts : 0; }
 
+// Debug / test hook (no device needed): the launcher's choice for a K/V sweep of `tiles` query tiles over Tk keys on a
+// machine of `sms` SMs -- 1: resident kernel, 0: pipelined kernel.
+int st_debug_attention_prefers_resident(long long tiles, int Tk, int sms) {
+  return (Tk > st::kAttnBlockKV && st::sweep_prefers_resident(tiles, Tk, sms)) ? 1 : 0;
+}
+
 // Debug / test hook: force one of the kernels behind st_attention_bf16 (0 = by shape, 1 two-CTA, 2 pipelined, 3 short,
 // 4 resident, 5 = by shape without the resident kernel; -1 = re-read ST_ATTN_IMPL).  Forcing a one-block kernel onto a longer K/V sweep is the caller's mistake.
 void st_debug_set_attention_impl(int impl) { st::g_attn_impl = (impl >= 0 && impl <= 5) ? impl : -1; }

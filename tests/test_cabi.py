@@ -73,3 +73,23 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_cabi.StableTritonError, match="no CPU or PyTorch fallback"):
         _cabi.lib()
+
+
+def test_attention_kernel_choice_model():
+    """The launcher sends a self-attention sweep to the resident kernel (three small CTAs per SM, every tile of the launch on
+    the machine at once) or to the pipelined one (owns an SM) from a cycle model calibrated on B200 -- pure host arithmetic,
+    checked here against the measured table in profiles/r02_attention_experiments.txt, section 9 (148 SMs)."""
+    import ctypes
+    from stabletriton_b200 import _cabi
+    f = _cabi._load().st_debug_attention_prefers_resident
+    f.restype, f.argtypes = ctypes.c_int, [ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+    tiles = lambda b, h, tq: b * h * ((tq + 127) // 128)
+    resident = [(2, 20, 1024, 1024), (3, 20, 1024, 1024), (4, 20, 1024, 1024), (16, 20, 1024, 1024), (2, 20, 1024, 256),
+                (2, 20, 1024, 512)]
+    pipelined = [(1, 20, 1024, 1024), (1, 37, 1024, 1024), (1, 5, 4096, 4096), (1, 10, 4096, 4096), (2, 10, 4096, 4096),
+                 (4, 10, 4096, 4096), (1, 10, 16384, 16384), (2, 10, 2048, 2048)]
+    for b, h, tq, tk in resident:
+        assert f(tiles(b, h, tq), tk, 148) == 1, (b, h, tq, tk)
+    for b, h, tq, tk in pipelined:
+        assert f(tiles(b, h, tq), tk, 148) == 0, (b, h, tq, tk)
+    assert f(320, 77, 148) == 0 and f(320, 128, 148) == 0  # one-block launches never reach the model
