@@ -351,7 +351,14 @@ int st_conv3x3_nhwc_bf16(const void* x, const void* w, const void* bias, void* y
   bool stream_k = false;
   bool pair = false;
   if (block_n == 0) {
-    const TileChoice tc = choose_tile(M, K, false, 9 * C, /*allow_pair=*/true);
+    static const bool conv_pairs = [] {  // ST_CONV_CLUSTER=0: no CTA pairs for the implicit-GEMM convolutions (A/B runs)
+      const char* e = getenv("ST_CONV_CLUSTER");
+      return !(e && e[0] == '0');
+    }();
+    // Measured inside the launch sequence of a step (profiles/r02_gemm_experiments.txt, 9): the pair kernel's k-block
+    // costs a convolution ~590 cycles at 256 x 160 (4-D A loads: 26 KB per CTA) against ~525 for the one-CTA kernel, so
+    // the GEMM-calibrated model over-rates pairs here; only the 256 x 256 pair tile of the 1280-filter levels pays.
+    const TileChoice tc = choose_tile(M, K, false, 9 * C, /*allow_pair=*/conv_pairs && K >= 1280);
     block_n = tc.block_n;
     pair = tc.pair;
     const long mb = (M + kGemmBlockM - 1) / kGemmBlockM;
