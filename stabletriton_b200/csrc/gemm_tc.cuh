@@ -574,6 +574,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (g == 0 && first_seg && warp == 2 && lane == 0) ST_TRACE(8);
         // All shared-memory reads of this chunk first (the compiler cannot hoist them over the staging
         // stores below: both live in shared memory), then straight-line register math on 32 columns.
+        uint4 rs[4];  // residual chunk from the staging tile the producer warp filled (columns past n_out hold TMA's zeros)
+        if (res_smem && has_res) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4)
+            rs[v4] = *reinterpret_cast<const uint4*>(
+                tail ? s_stage + tile_row * 64 + (v4 << 4)
+                     : s_stage + tile_row * 128 + (((half * 4 + v4) ^ (tile_row & 7)) << 4));
+        }
         float x[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -607,15 +615,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int e = 0; e < 32; ++e) x[e] = silu_f(x[e]);
         }
-        if (has_res) {
+        if (has_res && res_smem) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint32_t w[4] = {rs[j / 8].x, rs[j / 8].y, rs[j / 8].z, rs[j / 8].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              x[j + 2 * e] += __uint_as_float(w[e] << 16);
+              x[j + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            }
+          }
+        } else if (has_res) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8)
             if (n0 + c + j < p.n_out) {
-              const uint4 r4 =
-                  !res_smem ? res[g * 4 + j / 8]
-                            : *reinterpret_cast<const uint4*>(
-                                  tail ? s_stage + tile_row * 64 + ((j >> 3) << 4)
-                                       : s_stage + tile_row * 128 + (((half * 4 + (j >> 3)) ^ (tile_row & 7)) << 4));
+              const uint4 r4 = res[g * 4 + j / 8];
               const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
