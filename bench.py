@@ -512,7 +512,7 @@ def run_gpu_arm(args):
         roofline = {
             "bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all Linear + conv launches of one step)",
             "traffic_note": "dram read+write bytes per launch, mean over the 495 launches of one step, from the committed "
-                            "ncu capture profiles/r02_ncu_launch_summary_v2.json (ncu flushes L2 before every launch, so "
+                            "ncu capture profiles/r02_ncu_launch_summary_v4.json (ncu flushes L2 before every launch, so "
                             "activations are counted as DRAM reads: 5.1 GB of weights + 6.4 GB of activations per step)",
             "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops_sustained"], "traffic": ncu_gemm_traffic_per_launch(),
@@ -570,7 +570,7 @@ def run_gpu_arm(args):
 
 def ncu_gemm_traffic_per_launch():
     """DRAM bytes per GEMM launch from the committed ncu launch list (profiles/), or None if it is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_launch_summary_v2.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_launch_summary_v4.json")
     try:
         with open(path) as f:
             fam = json.load(f)["families"]["gemm_bf16_tc_kernel"]
