@@ -466,6 +466,31 @@ def test_outputs_do_not_overrun_and_repeat_bit_for_bit(K):
     guarded(lambda: K.layer_norm(xl, rnd(640, seed=21).cuda(), rnd(640, seed=22).cuda(), 1e-5))
 
 
+@pytest.mark.parametrize("m,k,n,block_n", [
+    (2048, 1280, 1280, 0), (2048, 320, 1280, 64), (2048, 320, 1280, 128), (2048, 320, 1280, 160), (2048, 320, 1280, 192),
+    (2048, 320, 1280, 256), (2048, 320, 1280, -160), (2048, 320, 1280, -256),
+    (8192, 640, 640, 0),      # two tiles per CTA: the first tile's residual by row loads, the last one's by TMA
+    (40000, 64, 320, 160),    # many tiles per CTA, one k-block each: the ring is still in its first pass when the residual lands
+    (300, 192, 328, 0), (130, 64, 72, 0), (257, 128, 200, 160),  # ragged rows / columns: boxes clipped on both edges
+])
+def test_linear_residual_tile_by_tma(K, m, k, n, block_n):
+    """The residual of a CTA's last output tile is fetched by TMA into the idle operand ring (same boxes / swizzle as the
+    store map) and added from there; earlier tiles of a multi-tile CTA use per-thread row loads.  Both against the oracle,
+    with the residual given as a column slice of a wider tensor (row pitch != N), for every tile width and for CTA pairs."""
+    x, w, b = rnd(m, k, seed=71), rnd(n, k, scale=k ** -0.5, seed=72), rnd(n, seed=73) * 0.1
+    wide = rnd(m, n + 24, seed=74)
+    r = wide[:, 16:16 + n]                      # pitch n + 24, 32-byte aligned start
+    ref = F.linear(x.float(), w.float(), b.float()) + r.float()
+    rc = wide.cuda()[:, 16:16 + n]
+    got = K.linear(x.cuda(), w.cuda(), b.cuda(), residual=rc, block_n=block_n)
+    check(got.cpu(), ref)
+    again = K.linear(x.cuda(), w.cuda(), b.cuda(), residual=rc, block_n=block_n)
+    assert torch.equal(got, again)
+    inplace = rc.clone()                        # residual aliasing the output: a tile is read and written by one CTA only
+    K.linear(x.cuda(), w.cuda(), b.cuda(), residual=inplace, block_n=block_n, out=inplace)
+    assert torch.equal(inplace, got)
+
+
 # ---- tile shapes of round 2: 160-wide tiles (32-column tail group) and CTA pairs (cta_group::2) -----------------------
 @pytest.mark.parametrize("m,k,n,block_n", [
     (2048, 1280, 1280, 160), (2048, 1280, 1280, -160), (2048, 5120, 1280, -160), (2048, 1280, 1280, -192),
