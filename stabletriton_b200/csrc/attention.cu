@@ -533,7 +533,11 @@ constexpr int kResSmemBytes = kAttnTileBytes + 2 * kResStages * kResKVBytes + 25
 constexpr int kResCtasPerSm = 3;
 constexpr float kResTau = 8.f;  // log2 units: the row reference moves when the block max exceeds it by more than 2^8
 
-__global__ void __launch_bounds__(kResThreads, kResCtasPerSm)
+// kCtas = 4: sized for four CTAs per SM (<= 96 registers): a thread keeps only 32 of its 64 scores -- the upper half is read
+// for the maximum, dropped, and read again from TMEM (P overwrites only the lower 32 columns) for its exponentials.  Chosen
+// for saturated launches (resident_four_ctas): more blocks per SM and second, at the price of a longer chain per CTA.
+template <int kCtas>
+__global__ void __launch_bounds__(kResThreads, kCtas)
 attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   constexpr int kStages = kResStages;
@@ -662,19 +666,41 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       tc_fence_after();
       if (j == 4 && warp == 1) RES_TRACE(2);
       if (j == 5 && warp == 1) RES_TRACE(12);
-      uint32_t s[64];
-      tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(s));
-      tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(s + 32));
-      tmem_ld_wait();
-      if (j == 4 && warp == 1) RES_TRACE(3);
-      if (valid < 64) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= valid) s[i] = 0xff800000u;  // -inf -> 2^(-inf) = 0
-      }
+      constexpr bool kReload = kCtas >= 4;
+      uint32_t s[kReload ? 32 : 64];  // kReload: the lower 32 columns; the upper 32 live in `hi` only while they are needed
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (kReload) {
+        uint32_t hi[32];
+        tmem_ld_32x32b_x32(t_s + 32, hi);
+        tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(s));
+        tmem_ld_wait();
+        if (valid < 64) {
 #pragma unroll
-      for (int i = 0; i < 64; i += 8) {
+          for (int i = 0; i < 32; ++i) {
+            if (i >= valid) s[i] = 0xff800000u;
+            if (32 + i >= valid) hi[i] = 0xff800000u;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx0 = max3f(mx0, __uint_as_float(hi[i]), __uint_as_float(hi[i + 1]));
+          mx1 = max3f(mx1, __uint_as_float(hi[i + 2]), __uint_as_float(hi[i + 3]));
+          mx2 = max3f(mx2, __uint_as_float(hi[i + 4]), __uint_as_float(hi[i + 5]));
+          mx3 = max3f(mx3, __uint_as_float(hi[i + 6]), __uint_as_float(hi[i + 7]));
+        }
+      } else {
+        tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(s));
+        tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(s + 32));
+        tmem_ld_wait();
+        if (valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) s[i] = 0xff800000u;  // -inf -> 2^(-inf) = 0
+        }
+      }
+      if (j == 4 && warp == 1) RES_TRACE(3);
+#pragma unroll
+      for (int i = 0; i < (kReload ? 32 : 64); i += 8) {
         mx0 = max3f(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
         mx1 = max3f(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
         mx2 = max3f(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
@@ -703,10 +729,20 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       if (j == 4 && warp == 1) RES_TRACE(4);
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
+        if (kReload && c == 32) {  // S columns [32, 64) again: P(j) so far covers columns [0, 16) only
+          tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(s));
+          tmem_ld_wait();
+          if (valid < 64) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (32 + i >= valid) s[i] = 0xff800000u;
+          }
+        }
+        const int sc = kReload ? 0 : c;
         float e[32];
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-          fma2_bcast(__uint_as_float(s[c + 2 * q]), __uint_as_float(s[c + 2 * q + 1]), p.scale_log2, neg_m, e[2 * q], e[2 * q + 1]);
+          fma2_bcast(__uint_as_float(s[sc + 2 * q]), __uint_as_float(s[sc + 2 * q + 1]), p.scale_log2, neg_m, e[2 * q], e[2 * q + 1]);
 #pragma unroll
         for (int i = 0; i < 32; ++i) e[i] = ex2_approx_ordered(e[i]);
         ready16(e, 0);
@@ -732,20 +768,22 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const float inv = 1.f / l;
     mbar_wait(o_full, 0);
     tc_fence_after();
-    uint32_t o[64];
-    tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(o));
-    tmem_ld_32x32b_x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(o + 32));
-    tmem_ld_wait();
-    if (q0 + row < p.Tq) {
-      __nv_bfloat16* orow = p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st;
+    __nv_bfloat16* orow = p.O + b * p.o_sb + h * p.o_sh + static_cast<long long>(q0 + row) * p.o_st;
 #pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-        uint4 ov;
-        ov.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
-        ov.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-        ov.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-        ov.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-        *reinterpret_cast<uint4*>(orow + i) = ov;
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(t_o + c, o);  // warp-collective: outside the row guard
+      tmem_ld_wait();
+      if (q0 + row < p.Tq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 ov;
+          ov.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+          ov.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          ov.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          ov.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c + i) = ov;
+        }
       }
     }
   }
@@ -1341,13 +1379,22 @@ static int make_tmap_bhtd(CUtensorMap* out, const void* base, int B, int H, int 
 // ~535 more per sibling CTA on its SM, an SM finishes one every ~940 cycles when it is full, + ~8.6 k once.  So the
 // resident kernel takes the short sweeps of more than two tiles per SM (T = 1024 self-attention: 320 tiles 28.4 -> 25.8 us,
 // 640 tiles 48 -> 42 us), the pipelined one the long sweeps (T >= 4096) and the launches of one or two rounds.
+// The resident kernel exists in two register budgets: three CTAs per SM (a thread keeps its 64 scores; the shorter chain --
+// launches of a few tiles per SM) and four (<= 96 registers: the upper 32 scores are re-read from TMEM; ~8 % more blocks per
+// SM and second once the machine is full: B16 T1024 138 -> 128 us, but B2 T1024 26 -> 33 us).
+static bool resident_four_ctas(long long tiles, int sms) { return tiles >= 8LL * sms; }
+
 static bool sweep_prefers_resident(long long tiles, int Tk, int sms) {
   const long long rounds = (tiles + sms - 1) / sms;
   const long long blocks128 = (Tk + kAttnBlockKV - 1) / kAttnBlockKV, blocks64 = (Tk + kResKV - 1) / kResKV;
   const long long pipelined = rounds * (blocks128 * 1450 + 7000);
   const long long siblings = (rounds < kResCtasPerSm ? rounds : kResCtasPerSm) - 1;
   const long long chain = blocks64 * (1750 + 535 * siblings), throughput = tiles * blocks64 * 940 / sms;
-  return (chain > throughput ? chain : throughput) + 8600 < pipelined;
+  if ((chain > throughput ? chain : throughput) + 8600 < pipelined) return true;
+  // saturated launches (>= 8 tiles per SM) of sweeps up to 4096 keys: the four-CTA form of the resident kernel finishes a
+  // 64-key block every ~715 cycles and SM + 2.8 k per tile, the pipelined kernel 2 x 702 per 128 keys + 8.6 k per tile
+  // (B4 T4096 248 -> 241 us, B16 T4096 961 -> 872 us; profiles/r02_attention_experiments.txt, 10)
+  return resident_four_ctas(tiles, sms) && blocks64 <= 64;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1413,8 +1460,10 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
     cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(attn_fwd_short_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(attn_fwd_resident_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    e = cudaFuncSetAttribute(attn_fwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemBytes);
+    cudaFuncSetAttribute(attn_fwd_resident_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(attn_fwd_resident_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(attn_fwd_resident_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_resident_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemBytes);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ST_ERR_CUDA;
@@ -1468,8 +1517,14 @@ int st_attention_bf16(const void* q, long long q_sb, long long q_sh, long long q
   // the phase stamps, the polynomial share and the ablation switches exist in the 8-exp-warp layout only
   const int parts = (trace || g_attn_poly == 2 || ablate) ? 2 : g_attn_parts;
   if (resident) {
-    launch_kernel(attn_fwd_resident_kernel, dim3(grid), dim3(kResThreads), kResSmemBytes, static_cast<cudaStream_t>(stream),
-                  tq, tk, tv, p);
+    static const int ctas_env = [] { const char* e = getenv("ST_ATTN_RES_CTAS"); return e ? atoi(e) : 0; }();  // 3 / 4: force
+    const bool four = ctas_env == 4 || (ctas_env != 3 && resident_four_ctas(tiles, device_sm_count()));
+    if (four)
+      launch_kernel(attn_fwd_resident_kernel<4>, dim3(grid), dim3(kResThreads), kResSmemBytes, static_cast<cudaStream_t>(stream),
+                    tq, tk, tv, p);
+    else
+      launch_kernel(attn_fwd_resident_kernel<3>, dim3(grid), dim3(kResThreads), kResSmemBytes, static_cast<cudaStream_t>(stream),
+                    tq, tk, tv, p);
     ST_CHECK_LAUNCH("attn_fwd_resident_kernel");
   } else if (pipelined && parts == 4) {
     launch_kernel(attn_fwd_pipelined_kernel<false, 4>, dim3(grid), dim3(A3Layout<4>::kThreads), kA3SmemBytes,
@@ -1508,7 +1563,8 @@ void st_debug_set_attention_parts(int parts) { st::g_attn_parts = (parts == 2 ||
 // Debug / test hook (no device needed): the launcher's choice for a K/V sweep of `tiles` query tiles over Tk keys on a
 // machine of `sms` SMs -- 1: resident kernel, 0: pipelined kernel.
 int st_debug_attention_prefers_resident(long long tiles, int Tk, int sms) {
-  return (Tk > st::kAttnBlockKV && st::sweep_prefers_resident(tiles, Tk, sms)) ? 1 : 0;
+  if (!(Tk > st::kAttnBlockKV && st::sweep_prefers_resident(tiles, Tk, sms))) return 0;
+  return st::resident_four_ctas(tiles, sms) ? 4 : 1;  // 4: the four-CTA form
 }
 
 // Debug / test hook: force one of the kernels behind st_attention_bf16 (0 = by shape, 1 two-CTA, 2 pipelined, 3 short,
@@ -1533,7 +1589,7 @@ int st_debug_attention_occupancy(void) {
   printf("attn kernel: regs %d, static smem %zu, max dyn smem %d, local %zu, occupancy @%d B: %d, @48K: %d, @0: %d\n",
          fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, st::kAttnSmemBytes, n, n48, n0);
   cudaFuncAttributes ra;
-  cudaFuncGetAttributes(&ra, st::attn_fwd_resident_kernel);
+  cudaFuncGetAttributes(&ra, st::attn_fwd_resident_kernel<3>);
   printf("resident kernel: regs %d, local %zu, dyn smem %d\n", ra.numRegs, ra.localSizeBytes, st::kResSmemBytes);
   return n;
 }

@@ -87,9 +87,11 @@ def test_attention_kernel_choice_model():
     resident = [(2, 20, 1024, 1024), (3, 20, 1024, 1024), (4, 20, 1024, 1024), (16, 20, 1024, 1024), (2, 20, 1024, 256),
                 (2, 20, 1024, 512)]
     pipelined = [(1, 20, 1024, 1024), (1, 37, 1024, 1024), (1, 5, 4096, 4096), (1, 10, 4096, 4096), (2, 10, 4096, 4096),
-                 (4, 10, 4096, 4096), (1, 10, 16384, 16384), (2, 10, 2048, 2048)]
+                 (1, 10, 16384, 16384), (2, 10, 2048, 2048)]
     for b, h, tq, tk in resident:
-        assert f(tiles(b, h, tq), tk, 148) == 1, (b, h, tq, tk)
+        assert f(tiles(b, h, tq), tk, 148) == (4 if tiles(b, h, tq) >= 8 * 148 else 1), (b, h, tq, tk)
+    for b, h, tq, tk in [(8, 20, 1024, 1024), (4, 10, 4096, 4096), (16, 10, 4096, 4096)]:  # saturated: the four-CTA form
+        assert f(tiles(b, h, tq), tk, 148) == 4, (b, h, tq, tk)
     for b, h, tq, tk in pipelined:
         assert f(tiles(b, h, tq), tk, 148) == 0, (b, h, tq, tk)
     assert f(320, 77, 148) == 0 and f(320, 128, 148) == 0  # one-block launches never reach the model

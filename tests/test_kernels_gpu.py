@@ -207,6 +207,30 @@ def test_attention_sweep_kernels_forced(K, impl, b, h, tq, tk, growth):
     assert torch.equal(got, again)
 
 
+def test_attention_resident_four_cta_form(K):
+    """Saturated sweeps (>= 8 query tiles per SM) take the four-CTA form of the resident kernel (upper half of the score row
+    re-read from tensor memory): same per-element arithmetic as the three-CTA form, so the outputs agree bit for bit -- checked
+    on a launch big enough to be sent there by shape (B = 8, 20 heads, T = 1024: 1280 tiles) against the forced pipelined kernel
+    and the oracle, ragged tail included."""
+    from stabletriton_b200 import _cabi
+    L = _cabi._load()
+    b, h, tq, tk = 8, 20, 1024, 1000
+    q, k, v = rnd(b, tq, h * 64, seed=81) * 1.5, rnd(b, tk, h * 64, seed=82) * 1.5, rnd(b, tk, h * 64, seed=83)
+    ramp = (1.0 + 5.0 * torch.arange(tk, dtype=torch.float32) / tk).view(1, tk, 1)
+    k = (k.float() * ramp).to(torch.bfloat16)
+    got = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)     # by shape: resident, four CTAs per SM
+    try:
+        L.st_debug_set_attention_impl(2)
+        pip = K.attention_btc(q.cuda(), k.cuda(), v.cuda(), h, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        L.st_debug_set_attention_impl(0)
+    ref = O.attention_core(q[:2].float(), k[:2].float(), v[:2].float(), h, 64)
+    check(got[:2].cpu(), ref, rel_tol=2e-2, cos_tol=0.9995)
+    rel, cos = parity(got.float(), pip.float())
+    assert rel <= 1e-2 and cos >= 0.99999, (rel, cos)
+
+
 def test_attention_long_sweep(K):
     """T = 16384 (the 2048^2 self-attention of SURVEY 8d config 5) against fp32 softmax(QK^T)V on the GPU, one head."""
     b, h, t = 1, 1, 16384
